@@ -1,0 +1,260 @@
+// Host side of libfcsa_b200.so: argument validation, TMA tensor-map construction, the
+// {f16, bf16} x {64, 128} switch and the kernel launches behind the C ABI of
+// include/fcsa_b200.h.
+//
+// Replaces the reference's host op + pybind layer (flash_cosine_sim_attention_cuda.cu:1630-1933)
+// and its dispatch macros (dispatch.h:38-73).  Differences by design: launches go to the
+// caller's stream and never synchronise (reference: legacy stream + cudaDeviceSynchronize,
+// cu:1720/1745/1889); errors are returned, not printed (cu:17-28); sm_100a only.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/fcsa_b200.h"
+#include "bwd_kernel.cuh"
+#include "fwd_kernel.cuh"
+#include "l2norm_kernels.cuh"
+#include "tensor_map.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(FCSA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_tensor(const fcsa_tensor* t, const char* name) {
+  if (!t || !t->ptr) return fail(FCSA_ERR_INVALID, "%s: null tensor", name);
+  if (!aligned16(t->ptr)) return fail(FCSA_ERR_INVALID, "%s: pointer not 16-byte aligned", name);
+  if ((t->sb % 8) || (t->sh % 8) || (t->sn % 8))
+    return fail(FCSA_ERR_INVALID, "%s: strides must be multiples of 8 elements (16 bytes)", name);
+  return FCSA_OK;
+}
+
+int check_problem(const fcsa_problem* p) {
+  if (!p) return fail(FCSA_ERR_INVALID, "null problem");
+  if (p->dtype != FCSA_F16 && p->dtype != FCSA_BF16)
+    return fail(FCSA_ERR_UNSUPPORTED, "dtype %d: only f16 and bf16 are implemented", p->dtype);
+  if (p->head_dim != 64 && p->head_dim != 128)
+    return fail(FCSA_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128 are implemented", p->head_dim);
+  if (p->batch <= 0 || p->heads <= 0 || p->seq_q <= 0 || p->seq_k <= 0)
+    return fail(FCSA_ERR_INVALID, "empty problem (batch %d heads %d seq_q %d seq_k %d)", p->batch,
+                p->heads, p->seq_q, p->seq_k);
+  if (p->kv_heads != p->heads && p->kv_heads != 1)
+    return fail(FCSA_ERR_INVALID, "kv_heads must equal heads or be 1 (got %d vs %d)", p->kv_heads,
+                p->heads);
+  if (p->causal && p->key_mask)
+    return fail(FCSA_ERR_INVALID, "mask should not be supplied if causality is needed");
+  return FCSA_OK;
+}
+
+template <typename T, int D>
+int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                   const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, cudaStream_t stream) {
+  using Cfg = fcsa::FwdCfg<D>;
+  const bool bf = p->dtype == FCSA_BF16;
+  CUtensorMap tq, tk, tv;
+  int r;
+  if ((r = fcsa::make_tensor_map_bhnd(&tq, q->ptr, bf, p->batch, p->heads, p->seq_q, D, q->sb, q->sh,
+                                      q->sn, 128)))
+    return fail(FCSA_ERR_CUDA, "cuTensorMapEncodeTiled(q) failed: %d", r);
+  if ((r = fcsa::make_tensor_map_bhnd(&tk, k->ptr, bf, p->batch, p->kv_heads, p->seq_k, D, k->sb,
+                                      k->sh, k->sn, 128)))
+    return fail(FCSA_ERR_CUDA, "cuTensorMapEncodeTiled(k) failed: %d", r);
+  if ((r = fcsa::make_tensor_map_bhnd(&tv, v->ptr, bf, p->batch, p->kv_heads, p->seq_k, D, v->sb,
+                                      v->sh, v->sn, 128)))
+    return fail(FCSA_ERR_CUDA, "cuTensorMapEncodeTiled(v) failed: %d", r);
+
+  fcsa::FwdArgs a;
+  a.B = p->batch;
+  a.H = p->heads;
+  a.Nq = p->seq_q;
+  a.Nk = p->seq_k;
+  a.causal = p->causal ? 1 : 0;
+  a.has_mask = p->key_mask ? 1 : 0;
+  a.kv_heads = p->kv_heads;
+  a.n_qblk = (p->seq_q + 255) / 256;
+  const float log2e = 1.4426950408889634f;
+  a.c1 = p->scale * log2e;
+  a.c2 = p->shift * log2e;
+  a.mask = p->key_mask;
+  a.mask_sb = p->key_mask_stride;
+  a.o = o->ptr;
+  a.o_sb = o->sb;
+  a.o_sh = o->sh;
+  a.o_sn = o->sn;
+  a.inv_l = inv_l;
+
+  auto kern = fcsa::fcsa_fwd_kernel<T, D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fwd)");
+    attr_set = true;
+  }
+  const long long grid = (long long)a.n_qblk * p->batch * p->heads;
+  if (grid > 0x7FFFFFFFLL) return fail(FCSA_ERR_INVALID, "problem too large for one launch");
+  kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(tq, tk, tv, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "forward kernel launch");
+  g_launches.fetch_add(1);
+  return FCSA_OK;
+}
+
+template <typename T>
+int launch_l2norm_fwd(const fcsa::L2Args& a, cudaStream_t stream) {
+  const int tpr = a.D / 8;
+  const int rows_per_block = 256 / tpr;
+  const long long rows = (long long)a.B * a.H * a.N;
+  const long long grid = (rows + rows_per_block - 1) / rows_per_block;
+  fcsa::l2norm_fwd_kernel<T><<<(unsigned)grid, 256, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "l2norm forward launch");
+  g_launches.fetch_add(1);
+  return FCSA_OK;
+}
+template <typename T>
+int launch_l2norm_bwd(const fcsa::L2Args& a, cudaStream_t stream) {
+  const int tpr = a.D / 8;
+  const int rows_per_block = 256 / tpr;
+  const long long rows = (long long)a.B * a.H * a.N;
+  const long long grid = (rows + rows_per_block - 1) / rows_per_block;
+  fcsa::l2norm_bwd_kernel<T><<<(unsigned)grid, 256, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "l2norm backward launch");
+  g_launches.fetch_add(1);
+  return FCSA_OK;
+}
+
+int check_l2(int32_t dtype, int32_t B, int32_t H, int32_t N, int32_t D, int32_t G) {
+  if (dtype != FCSA_F16 && dtype != FCSA_BF16)
+    return fail(FCSA_ERR_UNSUPPORTED, "l2norm: dtype %d not implemented", dtype);
+  if (B <= 0 || H <= 0 || N <= 0) return fail(FCSA_ERR_INVALID, "l2norm: empty tensor");
+  if (D != 32 && D != 64 && D != 128 && D != 256)
+    return fail(FCSA_ERR_UNSUPPORTED, "l2norm: head_dim %d not implemented", D);
+  if (G <= 0 || D % G != 0) return fail(FCSA_ERR_INVALID, "l2norm: groups %d does not divide %d", G, D);
+  const int gs = D / G;
+  if ((gs & (gs - 1)) != 0) return fail(FCSA_ERR_UNSUPPORTED, "l2norm: group size %d must be a power of two", gs);
+  return FCSA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fcsa_version(void) { return 100; }
+
+const char* fcsa_last_error(void) { return g_err; }
+
+int64_t fcsa_debug(void) { return g_launches.load(); }
+
+int fcsa_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                 const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, void* stream) {
+  int r;
+  if ((r = check_problem(p))) return r;
+  if ((r = check_tensor(q, "q")) || (r = check_tensor(k, "k")) || (r = check_tensor(v, "v")) ||
+      (r = check_tensor(o, "o")))
+    return r;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (p->dtype == FCSA_BF16) {
+    if (p->head_dim == 64) return launch_forward<__nv_bfloat16, 64>(p, q, k, v, o, inv_l, s);
+    return launch_forward<__nv_bfloat16, 128>(p, q, k, v, o, inv_l, s);
+  } else {
+    if (p->head_dim == 64) return launch_forward<__half, 64>(p, q, k, v, o, inv_l, s);
+    return launch_forward<__half, 128>(p, q, k, v, o, inv_l, s);
+  }
+}
+
+size_t fcsa_backward_workspace_bytes(const fcsa_problem* p) {
+  if (check_problem(p)) return 0;
+  return fcsa::bwd_workspace_bytes(p->batch, p->heads, p->kv_heads, p->seq_q, p->seq_k, p->head_dim);
+}
+
+int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                  const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
+                  const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
+                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream) {
+  int r;
+  if ((r = check_problem(p))) return r;
+  if ((r = check_tensor(q, "q")) || (r = check_tensor(k, "k")) || (r = check_tensor(v, "v")) ||
+      (r = check_tensor(o, "o")) || (r = check_tensor(d_o, "d_o")) || (r = check_tensor(dq, "dq")) ||
+      (r = check_tensor(dk, "dk")) || (r = check_tensor(dv, "dv")))
+    return r;
+  if (!inv_l) return fail(FCSA_ERR_INVALID, "inv_l: null");
+  const size_t need = fcsa_backward_workspace_bytes(p);
+  if (!workspace || workspace_bytes < need)
+    return fail(FCSA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  if (!aligned16(workspace)) return fail(FCSA_ERR_INVALID, "workspace not 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  fcsa::BwdHostArgs h;
+  h.dtype_bf16 = p->dtype == FCSA_BF16;
+  h.B = p->batch; h.H = p->heads; h.kv_heads = p->kv_heads; h.Nq = p->seq_q; h.Nk = p->seq_k;
+  h.D = p->head_dim; h.causal = p->causal ? 1 : 0;
+  h.scale = p->scale; h.shift = p->shift;
+  h.mask = p->key_mask; h.mask_sb = p->key_mask_stride;
+  h.q = *q; h.k = *k; h.v = *v; h.o = *o; h.d_o = *d_o; h.dq = *dq; h.dk = *dk; h.dv = *dv;
+  h.inv_l = inv_l;
+  h.workspace = workspace;
+  int launches = 0;
+  const char* err = nullptr;
+  cudaError_t ce = cudaSuccess;
+  r = fcsa::run_backward(h, s, &launches, &err, &ce);
+  g_launches.fetch_add(launches);
+  if (r == FCSA_ERR_CUDA) return fail(r, "%s: %s", err ? err : "backward", cudaGetErrorString(ce));
+  if (r != FCSA_OK) return fail(r, "%s", err ? err : "backward failed");
+  return FCSA_OK;
+}
+
+int fcsa_l2norm_forward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,
+                        int32_t groups, const fcsa_tensor* x, const fcsa_tensor* y, float* rnorm,
+                        void* stream) {
+  int r;
+  if ((r = check_l2(dtype, batch, heads, rows, head_dim, groups))) return r;
+  if ((r = check_tensor(x, "x")) || (r = check_tensor(y, "y"))) return r;
+  fcsa::L2Args a;
+  memset(&a, 0, sizeof(a));
+  a.B = batch; a.H = heads; a.N = rows; a.D = head_dim; a.G = groups;
+  a.x_sb = x->sb; a.x_sh = x->sh; a.x_sn = x->sn;
+  a.y_sb = y->sb; a.y_sh = y->sh; a.y_sn = y->sn;
+  a.x = x->ptr; a.y = y->ptr; a.rnorm = rnorm;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == FCSA_BF16 ? launch_l2norm_fwd<__nv_bfloat16>(a, s) : launch_l2norm_fwd<__half>(a, s);
+}
+
+int fcsa_l2norm_backward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows,
+                         int32_t head_dim, int32_t groups, const fcsa_tensor* dy,
+                         const fcsa_tensor* y, const float* rnorm, const fcsa_tensor* dx,
+                         void* stream) {
+  int r;
+  if ((r = check_l2(dtype, batch, heads, rows, head_dim, groups))) return r;
+  if ((r = check_tensor(dy, "dy")) || (r = check_tensor(y, "y")) || (r = check_tensor(dx, "dx")))
+    return r;
+  if (!rnorm) return fail(FCSA_ERR_INVALID, "rnorm: null");
+  fcsa::L2Args a;
+  memset(&a, 0, sizeof(a));
+  a.B = batch; a.H = heads; a.N = rows; a.D = head_dim; a.G = groups;
+  a.x_sb = dy->sb; a.x_sh = dy->sh; a.x_sn = dy->sn;
+  a.y_sb = y->sb; a.y_sh = y->sh; a.y_sn = y->sn;
+  a.o_sb = dx->sb; a.o_sh = dx->sh; a.o_sn = dx->sn;
+  a.x = dy->ptr; a.y = y->ptr; a.dx = dx->ptr; a.rnorm = const_cast<float*>(rnorm);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == FCSA_BF16 ? launch_l2norm_bwd<__nv_bfloat16>(a, s) : launch_l2norm_bwd<__half>(a, s);
+}
+
+}  // extern "C"

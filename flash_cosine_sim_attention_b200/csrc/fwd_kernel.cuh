@@ -1,0 +1,325 @@
+// Forward kernel: o = (sum_j exp(scale*q.k_j - shift) v_j) / max(sum_j exp(..), 1e-10)
+//
+// Replaces the reference's forward_kernel (flash_cosine_sim_attention_cuda.cu:1072-1247).
+// Same math (fixed shift instead of a running row max, cu:1216; running row sum, cu:1236;
+// final 1/max(l, eps) scaling, cu:1239-1246; bottom-right aligned causal mask, cu:1097/1210;
+// key-padding mask, cu:1198-1212) - completely different machine mapping:
+//
+//   * one CTA owns 256 query rows of one (batch, head): two 128-row tiles that ping-pong
+//   * warp 8   : TMA producer   (Q once, K and V tiles through mbarrier rings)
+//   * warp 9   : tcgen05 issuer (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with P_t read from TMEM)
+//   * warps 0-3: "softmax" warpgroup for tile 0, warps 4-7 for tile 1: thread == query row,
+//                tcgen05.ld S -> exp2(fma) -> row sum in a register -> 16-bit P -> tcgen05.st
+//   * TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P_t aliases the
+//     upper half of S_t (64 columns of packed 16-bit pairs).  Because there is no row max
+//     there is no rescaling of O: the accumulator never leaves TMEM until the epilogue.
+#pragma once
+
+#include "sm100_primitives.cuh"
+
+namespace fcsa {
+
+struct FwdArgs {
+  int B, H, Nq, Nk;
+  int causal;        // bottom-right aligned: key j visible to query i iff j <= i + (Nk - Nq)
+  int has_mask;      // key padding mask (B, Nk), nonzero = keep
+  int kv_heads;      // 1 => keys/values shared by all heads, else == H
+  int n_qblk;        // ceil(Nq / 256)
+  float c1;          // scale * log2(e)
+  float c2;          // shift * log2(e)
+  const uint8_t* mask;
+  long long mask_sb;
+  void* o;
+  long long o_sb, o_sh, o_sn;   // element strides of o (feature dim contiguous)
+  float* inv_l;                 // (B, H, Nq) fp32, contiguous
+};
+
+template <int D>
+struct FwdCfg {
+  static constexpr int kTile = 128 * D * 2;          // bytes of one 128-row operand tile
+  static constexpr int kKS = (D == 64) ? 3 : 2;       // K ring depth
+  static constexpr int kVS = (D == 64) ? 3 : 2;       // V ring depth
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = 2 * kTile;
+  static constexpr int kOffV = kOffK + kKS * kTile;
+  static constexpr int kOffBar = kOffV + kVS * kTile;
+  static constexpr int kSmem = kOffBar + 256 + 1024;  // + alignment slack
+  static constexpr int kThreads = 320;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(320, 1)
+fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const FwdArgs a) {
+  using Cfg = FwdCfg<D>;
+  constexpr int KS = Cfg::kKS, VS = Cfg::kVS, TILE = Cfg::kTile;
+  constexpr int DCH = D / 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ);
+  const uint32_t sK = smem_u32(smem + Cfg::kOffK);
+  const uint32_t sV = smem_u32(smem + Cfg::kOffV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  // barrier indices
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS,
+                V_EMPTY = V_FULL + VS, S_FULL = V_EMPTY + VS, P_FULL = S_FULL + 2,
+                O_FULL = P_FULL + 2, NBARS = O_FULL + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which work item ---------------------------------------------------------------
+  const int bh_count = a.B * a.H;
+  const int rank = blockIdx.x / bh_count;
+  const int bh = blockIdx.x - rank * bh_count;
+  const int qblk = a.causal ? (a.n_qblk - 1 - rank) : rank;   // heaviest causal blocks first
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int hk = (a.kv_heads == 1) ? 0 : h;
+  const int m0 = qblk * 256;
+  const int off = a.Nk - a.Nq;
+  const int nkt = (a.Nk + 127) >> 7;
+  int n_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int row_lo = m0 + 128 * t;
+    if (row_lo >= a.Nq) {
+      n_t[t] = 0;
+    } else if (!a.causal) {
+      n_t[t] = nkt;
+    } else {
+      const int row_hi = min(row_lo + 127, a.Nq - 1);
+      const int last_col = row_hi + off;
+      n_t[t] = last_col < 0 ? 0 : min(nkt, (last_col >> 7) + 1);
+    }
+  }
+  const int NT = max(n_t[0], n_t[1]);
+
+  // ---- one-time setup ------------------------------------------------------------------
+  if (warp == 8 && elect_one()) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(BAR(Q_FULL), 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(BAR(K_FULL + i), 1);
+      mbar_init(BAR(K_EMPTY + i), 1);
+    }
+    for (int i = 0; i < VS; ++i) {
+      mbar_init(BAR(V_FULL + i), 1);
+      mbar_init(BAR(V_EMPTY + i), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(BAR(S_FULL + t), 1);
+      mbar_init(BAR(P_FULL + t), 128);
+      mbar_init(BAR(O_FULL + t), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // =============================== TMA producer ===============================
+    // (elect_one, not lane == 0: ptxas then keeps descriptors/addresses in uniform registers
+    //  instead of wrapping every UTMALDG/UTCHMMA in a divergence "waterfall" loop)
+    if (elect_one()) {
+      mbar_expect_tx(BAR(Q_FULL), 2 * TILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int ch = 0; ch < DCH; ++ch)
+          tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL), ch * 64, m0 + 128 * t, h, b);
+      for (int j = 0; j < NT; ++j) {
+        const int ks = j % KS, vs = j % VS;
+        mbar_wait(BAR(K_EMPTY + ks), ((j / KS) & 1) ^ 1);
+        mbar_expect_tx(BAR(K_FULL + ks), TILE);
+#pragma unroll
+        for (int ch = 0; ch < DCH; ++ch)
+          tma_load_4d(sK + ks * TILE + ch * 16384, &tm_k, BAR(K_FULL + ks), ch * 64, j * 128, hk, b);
+        mbar_wait(BAR(V_EMPTY + vs), ((j / VS) & 1) ^ 1);
+        mbar_expect_tx(BAR(V_FULL + vs), TILE);
+#pragma unroll
+        for (int ch = 0; ch < DCH; ++ch)
+          tma_load_4d(sV + vs * TILE + ch * 16384, &tm_v, BAR(V_FULL + vs), ch * 64, j * 128, hk, b);
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer =================================
+    if (NT > 0 && elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc<T>(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc<T>(128, D, 0, 1);
+      mbar_wait(BAR(Q_FULL), 0);
+      tc_fence_after();
+
+      auto issue_S = [&](int t, int j) {
+        const int ks = j % KS;
+        mbar_wait(BAR(K_FULL + ks), (j / KS) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t o = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(tmem + t * 128, umma_desc_sw128(sQ + t * TILE + o, 16, 1024),
+                  umma_desc_sw128(sK + ks * TILE + o, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(BAR(S_FULL + t));
+      };
+
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (n_t[t] > 0) issue_S(t, 0);
+      umma_commit(BAR(K_EMPTY + 0));
+
+      for (int j = 0; j < NT; ++j) {
+        const int vs = j % VS;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (j < n_t[t]) {
+            mbar_wait(BAR(P_FULL + t), j & 1);
+            mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              umma_ts(tmem + 256 + t * D, tmem + t * 128 + 64 + k * 8,
+                      umma_desc_sw128(sV + vs * TILE + k * 2048, 16384, 1024), idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
+            }
+            if (j + 1 < n_t[t]) issue_S(t, j + 1);
+            else umma_commit(BAR(O_FULL + t));
+          }
+        }
+        umma_commit(BAR(V_EMPTY + vs));
+        if (j + 1 < NT) umma_commit(BAR(K_EMPTY + (j + 1) % KS));
+      }
+    }
+  } else {
+    // =============================== softmax warpgroups =========================
+    const int t = warp >> 2;                 // which 128-row tile
+    const int wq = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int r = wq * 32 + lane;            // row inside the tile
+    const int row_g = m0 + 128 * t + r;      // global query row
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t tS = lane_base + t * 128;
+    const uint32_t tP = tS + 64;
+    const uint32_t tO = lane_base + 256 + t * D;
+    const int nt = n_t[t];
+    const float c1 = a.c1, nc2 = -a.c2;
+    float l = 0.f;
+
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(BAR(S_FULL + t), j & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_x32(tS + 0, s0);
+      tmem_ld_x32(tS + 32, s1);
+      tmem_ld_x32(tS + 64, s2);
+      tmem_ld_x32(tS + 96, s3);
+      tmem_ld_wait();
+
+      const int col0 = j * 128;
+      const bool need_mask = a.has_mask || (col0 + 127 >= a.Nk) ||
+                             (a.causal && (col0 + 127 > m0 + 128 * t + off));
+      if (!need_mask) {
+        auto chunk = [&](const uint32_t(&s)[32], int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c1, nc2));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c1, nc2));
+            l += p0 + p1;
+            pk[i] = pack2<T>(p0, p1);
+          }
+          tmem_st_x16(tP + c * 16, pk);
+        };
+        chunk(s0, 0);
+        chunk(s1, 1);
+        chunk(s2, 2);
+        chunk(s3, 3);
+      } else {
+        // visible iff column <= lim (causal / ragged end) and key-mask bit set
+        int lim = a.Nk - 1;
+        if (a.causal) lim = min(lim, row_g + off);
+        lim -= col0;
+        uint32_t kw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (a.has_mask) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int col = col0 + w * 32 + lane;
+            const uint8_t mv = (col < a.Nk) ? a.mask[(long long)b * a.mask_sb + col] : uint8_t(0);
+            kw[w] = __ballot_sync(0xFFFFFFFFu, mv != 0);
+          }
+        }
+        auto chunk = [&](const uint32_t(&s)[32], int c) {
+          uint32_t pk[16];
+          const uint32_t word = kw[c];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int cc0 = c * 32 + 2 * i, cc1 = cc0 + 1;
+            float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c1, nc2));
+            float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c1, nc2));
+            p0 = (cc0 <= lim && ((word >> (2 * i)) & 1u)) ? p0 : 0.f;
+            p1 = (cc1 <= lim && ((word >> (2 * i + 1)) & 1u)) ? p1 : 0.f;
+            l += p0 + p1;
+            pk[i] = pack2<T>(p0, p1);
+          }
+          tmem_st_x16(tP + c * 16, pk);
+        };
+        chunk(s0, 0);
+        chunk(s1, 1);
+        chunk(s2, 2);
+        chunk(s3, 3);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(BAR(P_FULL + t));
+    }
+
+    // ---- epilogue: O * 1/max(l, eps) -> global ----------------------------------------
+    const float inv = 1.0f / fmaxf(l, 1e-10f);
+    const bool row_ok = row_g < a.Nq;
+    T* orow = reinterpret_cast<T*>(a.o) + (long long)b * a.o_sb + (long long)h * a.o_sh +
+              (long long)row_g * a.o_sn;
+    if (nt > 0) {
+      mbar_wait(BAR(O_FULL + t), 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_x32(tO + c * 32, acc);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 w;
+            w.x = pack2<T>(__uint_as_float(acc[8 * v + 0]) * inv, __uint_as_float(acc[8 * v + 1]) * inv);
+            w.y = pack2<T>(__uint_as_float(acc[8 * v + 2]) * inv, __uint_as_float(acc[8 * v + 3]) * inv);
+            w.z = pack2<T>(__uint_as_float(acc[8 * v + 4]) * inv, __uint_as_float(acc[8 * v + 5]) * inv);
+            w.w = pack2<T>(__uint_as_float(acc[8 * v + 6]) * inv, __uint_as_float(acc[8 * v + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + v * 8) = w;
+          }
+        }
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int v = 0; v < D / 8; ++v) *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (row_ok && a.inv_l != nullptr)
+      a.inv_l[((long long)b * a.H + h) * a.Nq + row_g] = inv;
+  }
+
+  // ---- teardown ------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fcsa

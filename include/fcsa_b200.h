@@ -1,0 +1,132 @@
+/*
+ * fcsa_b200.h - C ABI of libfcsa_b200.so, the B200 (sm_100a) fused cosine-similarity
+ * attention library.
+ *
+ * This is the drop-in boundary for the reference's CUDA extension
+ * (lucidrains/flash-cosine-sim-attention @ v0.1.40).  Each entry point names the reference
+ * interface it replaces (file:line, paths relative to the reference repository):
+ *
+ *   fcsa_forward            <- flash_cosine_sim_attention_forward   flash_cosine_sim_attention_cuda.cu:1630-1748
+ *                              (pybind `forward`, cu:1928-1933; called from flash_cosine_sim_attention.py:247-256)
+ *   fcsa_backward           <- flash_cosine_sim_attention_backward  cu:1752-1917
+ *                              (pybind `backward`; called from flash_cosine_sim_attention.py:281-302)
+ *   fcsa_debug              <- debug()                              cu:1921
+ *   fcsa_l2norm_forward /   <- l2norm / grouped_l2norm / l2norm_tensors  flash_cosine_sim_attention.py:38-65
+ *   fcsa_l2norm_backward       (PyTorch F.normalize + autograd in the reference; fused kernels here)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every tensor is a DEVICE pointer to 16-bit data (FCSA_F16 / FCSA_BF16) addressed as
+ *     [batch][head][row][feature] with element strides (sb, sh, sn) and a contiguous feature
+ *     dimension; pointers and strides*2 must be multiples of 16 bytes (TMA requirement)
+ *   - `stream` is a cudaStream_t; all work is enqueued on it and nothing synchronises
+ *     (the reference device-synchronised after every call, cu:1745/1889 - deliberately not kept)
+ *   - inputs are borrowed and never written; outputs are caller-allocated
+ *   - return value: FCSA_OK or an error code; fcsa_last_error() returns a thread-local message
+ *     (the reference only printed CUDA errors to stderr, cu:17-28)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ */
+#ifndef FCSA_B200_H
+#define FCSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FCSA_F16 = 0, FCSA_BF16 = 1 };
+
+enum {
+  FCSA_OK = 0,
+  FCSA_ERR_INVALID = 1,      /* bad argument (shape, alignment, null pointer)           */
+  FCSA_ERR_UNSUPPORTED = 2,  /* valid request this build has no kernel for              */
+  FCSA_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed                     */
+  FCSA_ERR_WORKSPACE = 4     /* workspace too small                                     */
+};
+
+/* A (batch, head, row, feature) view with a contiguous feature dimension. */
+typedef struct fcsa_tensor {
+  void* ptr;
+  int64_t sb, sh, sn; /* element strides of batch, head, row */
+} fcsa_tensor;
+
+/*
+ * One attention problem.  Mirrors the argument list of the reference's forward/backward
+ * (cu:1630-1639, cu:1752-1764) after its shape canonicalisation (cu:1647-1660):
+ *   - merged batch-heads (3-D q) is expressed as heads = 1
+ *   - single-head keys/values (3-D k, v with 4-D q; cu:1679) is kv_heads = 1
+ */
+typedef struct fcsa_problem {
+  int32_t dtype;     /* FCSA_F16 | FCSA_BF16 (q, k, v, o, do, dq, dk, dv all share it)        */
+  int32_t batch;
+  int32_t heads;
+  int32_t kv_heads;  /* == heads, or 1 for keys/values shared across heads                   */
+  int32_t seq_q;
+  int32_t seq_k;
+  int32_t head_dim;  /* 64 or 128                                                             */
+  int32_t causal;    /* bottom-right aligned (cu:1097, cu:1210): key j visible iff j <= i + seq_k - seq_q */
+  float scale;       /* logits = scale * <q, k>                                               */
+  float shift;       /* p = exp(logit - shift); the reference uses shift = scale (cu:1216)    */
+  const uint8_t* key_mask;   /* (batch, seq_k) bytes, nonzero = attend; NULL = no mask (cu:1198-1212) */
+  int64_t key_mask_stride;   /* bytes between batches                                         */
+} fcsa_problem;
+
+/* Library / ABI version: major*10000 + minor*100 + patch. */
+int fcsa_version(void);
+
+/* Message describing the last error on the calling thread ("" if none). */
+const char* fcsa_last_error(void);
+
+/* Reference `debug()` (cu:1921): a no-op hook.  Here it returns the number of kernels this
+ * library has launched in the current process (bench.py reports it as gpu_launches). */
+int64_t fcsa_debug(void);
+
+/*
+ * o = softmax-like(q k^T) v with the fixed-shift formulation; inv_l[b][h][i] = 1 / max(l_i, 1e-10)
+ * is the saved normaliser the backward needs (the reference's `l` output, cu:1698/1239).
+ * inv_l: (batch, heads, seq_q) fp32 contiguous, may be NULL when no backward will follow.
+ * mask and causal are mutually exclusive (flash_cosine_sim_attention.py:88, cu:1675).
+ * Rows with no visible key produce o = 0 (cu:1239, reference behaviour of the fused kernel).
+ */
+int fcsa_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                 const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, void* stream);
+
+/* Bytes of scratch fcsa_backward needs for this problem (fp32 dq / shared-kv accumulators, delta). */
+size_t fcsa_backward_workspace_bytes(const fcsa_problem* p);
+
+/*
+ * Gradients of fcsa_forward w.r.t. q, k, v (the q, k given are the already-normalised ones,
+ * exactly as in the reference: cu:1487-1626).  dq/dk/dv are caller-allocated in the problem
+ * dtype; with kv_heads == 1, dk/dv have a single head and receive the sum over heads
+ * (cu:1613-1619).  `workspace` must hold fcsa_backward_workspace_bytes(p) bytes.
+ */
+int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                  const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
+                  const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
+                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * y = x / max(||x||_2, 1e-12) over `groups` equal chunks of the feature dimension
+ * (flash_cosine_sim_attention.py:38-55).  x: strided view; y: same shape (any strides);
+ * rnorm: (batch, heads, rows, groups) fp32 contiguous = 1 / max(||x||, eps), may be NULL.
+ */
+int fcsa_l2norm_forward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,
+                        int32_t groups, const fcsa_tensor* x, const fcsa_tensor* y, float* rnorm,
+                        void* stream);
+
+/*
+ * dx = (dy - y <y, dy>_group) * rnorm_group : the l2norm backward given the NORMALISED y.
+ * dy, y, dx: 16-bit strided views.
+ */
+int fcsa_l2norm_backward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows,
+                         int32_t head_dim, int32_t groups, const fcsa_tensor* dy,
+                         const fcsa_tensor* y, const float* rnorm, const fcsa_tensor* dx,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FCSA_B200_H */
