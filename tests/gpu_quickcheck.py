@@ -62,7 +62,7 @@ def run(mode):
                                mask=None if mask is None else mask.numpy(),
                                d_out=do.float().numpy() if want_bwd else None, empty_rows="zero", **kw)
         refs = ref if want_bwd else (ref,)
-        gots = [o.float().cpu().numpy()] + (grads or [])
+        gots = [o.detach().float().cpu().numpy()] + (grads or [])
         line = f"{name:24s} {str(dtype)[6:]:9s}"
         for nm, got, rf in zip(("o", "dq", "dk", "dv"), gots, refs):
             err = np.abs(got - rf).max()

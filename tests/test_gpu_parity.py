@@ -1,0 +1,274 @@
+"""GPU parity tests (run on the B200 with `pytest -m gpu`): the CUDA path - reached through the
+public Python API, i.e. ctypes -> C ABI -> sm_100a kernels - against the float64 oracle on the
+same (already rounded) inputs, against the committed reference golden vectors, and through
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerance policy (floating point; stated per test):
+  max |got - ref| <= tol * max |ref|, tol = 1e-2 for bf16 and 2e-3 for f16 outputs, 2e-2 / 4e-3
+  for gradients (they pass through two more 16-bit roundings: P/dS operands and the stored
+  normalised q, k).  The reference's own tests allow 1e-1 absolute in f16 (tests/test.py:12-18,49).
+"""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cosine_sim_attention_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_OUT = {torch.bfloat16: 1e-2, torch.float16: 2e-3}
+TOL_GRAD = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
+BWD_HEAD_DIMS = (64,)
+
+
+@pytest.fixture(scope="module")
+def fcsa():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import flash_cosine_sim_attention_b200 as pkg
+    from flash_cosine_sim_attention_b200 import _abi
+    _abi.load()            # fail loudly if the native library did not travel
+    return pkg
+
+
+def rel_err(got, ref):
+    got = got.detach().float().cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all(), "NaN/Inf in CUDA result"
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+def make_inputs(qs, kvs, dtype, seed, mask_p=None, amp=1.0):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(qs, generator=g) * amp).to(dtype)
+    k = (torch.randn(kvs, generator=g) * amp).to(dtype)
+    v = torch.randn(kvs, generator=g).to(dtype)
+    do = torch.randn(qs, generator=g).to(dtype)
+    mask = None
+    if mask_p is not None:
+        mask = torch.rand((qs[0], kvs[-2]), generator=g) > mask_p
+        mask[:, 0] = True
+    return q, k, v, do, mask
+
+
+def check(fcsa, qs, kvs, dtype, seed=0, mask_p=None, grads=True, amp=1.0, **kw):
+    q, k, v, do, mask = make_inputs(qs, kvs, dtype, seed, mask_p, amp)
+    dev = "cuda"
+    grads = grads and qs[-1] in BWD_HEAD_DIMS
+    qd, kd, vd = (t.to(dev).requires_grad_(grads) for t in (q, k, v))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, mask=None if mask is None else mask.to(dev), **kw)
+    assert o.shape == q.shape and o.dtype == dtype
+    ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(),
+                           mask=None if mask is None else mask.numpy(),
+                           d_out=do.float().numpy() if grads else None, empty_rows="zero", **kw)
+    if not grads:
+        assert rel_err(o, ref) <= TOL_OUT[dtype]
+        return
+    o.backward(do.to(dev))
+    assert rel_err(o, ref[0]) <= TOL_OUT[dtype], "o"
+    for name, t, r in (("dq", qd, ref[1]), ("dk", kd, ref[2]), ("dv", vd, ref[3])):
+        assert t.grad.shape == t.shape and t.grad.dtype == dtype
+        assert rel_err(t.grad, r) <= TOL_GRAD[dtype], name
+
+
+# ---- the reference's own test grid (tests/test.py:31-125), on the dtypes/head dims the kernels cover,
+# ---- plus bf16 and MQA gradients which the reference never tested -----------------------------------
+@pytest.mark.parametrize("causal,mask", [(True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("seq_len", [63, 127])
+@pytest.mark.parametrize("dim_head", [64, 128])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("single_head_kv", [False, True])
+def test_reference_grid(fcsa, causal, mask, seq_len, dim_head, dtype, single_head_kv):
+    batch, heads = 4, 8
+    kvs = (batch, seq_len, dim_head) if single_head_kv else (batch, heads, seq_len, dim_head)
+    check(fcsa, (batch, heads, seq_len, dim_head), kvs, dtype, seed=seq_len + dim_head,
+          mask_p=0.5 if mask else None, causal=causal)
+
+
+# ---- committed golden vectors produced by the unmodified reference --------------------------------
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_reference_golden_vectors(fcsa, path):
+    z = np.load(path)
+    kw = ast.literal_eval(str(z["kwargs"]))
+    mask = torch.from_numpy(z["mask"]).cuda() if z["mask"].size else None
+    dt = torch.bfloat16     # the golden inputs are bf16-representable by construction
+    grads = z["q"].shape[-1] in BWD_HEAD_DIMS
+    q, k, v = (torch.from_numpy(z[n]).to(dt).cuda().requires_grad_(grads) for n in ("q", "k", "v"))
+    assert np.array_equal(q.detach().float().cpu().numpy(), z["q"])
+    o = fcsa.flash_cosine_sim_attention(q, k, v, mask=mask, **kw)
+    assert rel_err(o, z["o"]) <= TOL_OUT[dt]
+    if grads:
+        o.backward(torch.from_numpy(z["d_out"]).to(dt).cuda())
+        for name, t in (("dq", q), ("dk", k), ("dv", v)):
+            assert rel_err(t.grad, z[name]) <= TOL_GRAD[dt], name
+
+
+# ---- features the reference never tested (SURVEY.md par. 4) ----------------------------------------
+@pytest.mark.parametrize("qn,kn", [(200, 456), (456, 200), (129, 129), (1, 300), (257, 1)])
+def test_causal_cross_lengths(fcsa, qn, kn):
+    check(fcsa, (2, 2, qn, 64), (2, 2, kn, 64), torch.bfloat16, seed=qn, causal=True)
+
+
+@pytest.mark.parametrize("groups,scale", [(2, 8), (4, 10), (8, 1), (16, 4)])
+def test_groups_and_scales(fcsa, groups, scale):
+    check(fcsa, (1, 4, 300, 64), (1, 4, 300, 64), torch.float16, seed=groups, groups=groups, scale=scale)
+
+
+def test_merged_batch_heads(fcsa):
+    check(fcsa, (6, 260, 64), (6, 260, 64), torch.bfloat16, seed=7, causal=True)
+
+
+def test_no_l2norm(fcsa):
+    check(fcsa, (1, 2, 200, 64), (1, 2, 200, 64), torch.bfloat16, seed=8, amp=0.2, l2norm_qk=False, scale=1)
+
+
+def test_l2norm_groups_alias(fcsa):
+    q, k, v, _, _ = make_inputs((1, 2, 130, 64), (1, 2, 130, 64), torch.float16, 9)
+    a = fcsa.flash_cosine_sim_attention(q.cuda(), k.cuda(), v.cuda(), groups=4)
+    b = fcsa.flash_cosine_sim_attention(q.cuda(), k.cuda(), v.cuda(), l2norm_groups=4)
+    assert torch.equal(a, b)
+
+
+def test_strided_inputs_as_in_transformer(fcsa):
+    """transformer.py hands the op 'b n (h d) -> b h n d' views (reference transformer.py:100)."""
+    g = torch.Generator().manual_seed(10)
+    dt = torch.bfloat16
+    base = [torch.randn(2, 300, 4 * 64, generator=g).to(dt) for _ in range(3)]
+    views = [t.view(2, 300, 4, 64).permute(0, 2, 1, 3) for t in base]
+    assert not views[0].is_contiguous()
+    qd, kd, vd = (t.cuda().view(2, 300, 4, 64).permute(0, 2, 1, 3).requires_grad_() for t in base)
+    do = torch.randn(2, 4, 300, 64, generator=g).to(dt)
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, causal=True)
+    o.backward(do.cuda())
+    ref = oracle.attention(*(t.float().numpy() for t in views), causal=True, d_out=do.float().numpy())
+    assert rel_err(o, ref[0]) <= TOL_OUT[dt]
+    for t, r in zip((qd, kd, vd), ref[1:]):
+        assert rel_err(t.grad, r) <= TOL_GRAD[dt]
+
+
+def test_sum_backward_broadcast_grad(fcsa):
+    """`o.sum().backward()` (reference tests and benchmark helper) delivers a stride-0 grad."""
+    q, k, v, _, _ = make_inputs((1, 2, 150, 64), (1, 2, 150, 64), torch.float16, 11)
+    qd, kd, vd = (t.cuda().requires_grad_() for t in (q, k, v))
+    fcsa.flash_cosine_sim_attention(qd, kd, vd).sum().backward()
+    ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(),
+                           d_out=np.ones((1, 2, 150, 64)))
+    for t, r in zip((qd, kd, vd), ref[1:]):
+        assert rel_err(t.grad, r) <= TOL_GRAD[torch.float16]
+
+
+def test_fully_masked_rows_give_zero(fcsa):
+    """Documented divergence from the naive formulation (reference cu:1239): o = 0, grads = 0."""
+    q, k, v, do, _ = make_inputs((2, 2, 70, 64), (2, 2, 90, 64), torch.bfloat16, 12)
+    mask = torch.ones(2, 90, dtype=torch.bool)
+    mask[1] = False
+    qd, kd, vd = (t.cuda().requires_grad_() for t in (q, k, v))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, mask=mask.cuda())
+    o.backward(do.cuda())
+    assert torch.all(o[1] == 0) and torch.isfinite(o).all()
+    for t in (qd, kd, vd):
+        assert torch.isfinite(t.grad).all() and torch.all(t.grad[1] == 0)
+
+
+def test_forward_only_under_no_grad_and_ragged_generate_lengths(fcsa):
+    """`generate` calls the op with a different, unaligned N every step (transformer.py:167-181)."""
+    for n in (1, 7, 64, 65, 255, 256, 257):
+        check(fcsa, (1, 2, n, 64), (1, 2, n, 64), torch.float16, seed=n, grads=False, causal=True)
+
+
+def test_reference_extension_surface(fcsa):
+    """forward / backward / debug with the reference's pybind signatures (cu:1630, 1752, 1921)."""
+    from importlib import import_module
+    m = import_module("flash_cosine_sim_attention_b200.flash_cosine_sim_attention")
+    q, k, v, do, _ = make_inputs((1, 2, 140, 64), (1, 2, 140, 64), torch.float16, 13)
+    qn, kn = fcsa.l2norm_tensors(q.cuda(), k.cuda())
+    qn.requires_grad_()
+    o, inv_l, should_backwards = m.forward(qn, kn, v.cuda(), None, None, False, 8.0, True)
+    assert should_backwards and inv_l.shape == (1, 2, 140) and inv_l.dtype == torch.float32
+    dq, dk, dv, db = m.backward(do.cuda(), o, inv_l, qn.detach(), kn, v.cuda(), None, None, False, 8.0, True)
+    assert db is None and dq.shape == q.shape
+    qn64, kn64 = (oracle.l2norm(t.float().numpy())[0] for t in (q, k))
+    ref = oracle.attention(qn.detach().float().cpu().numpy(), kn.float().cpu().numpy(), v.float().numpy(),
+                           causal=True, l2norm_qk=False, d_out=do.float().numpy())
+    assert rel_err(o, ref[0]) <= TOL_OUT[torch.float16]
+    assert rel_err(dq, ref[1]) <= TOL_GRAD[torch.float16]
+    assert np.abs(qn.detach().float().cpu().numpy() - qn64).max() < 1e-3
+    assert m.debug() > 0
+
+
+def test_l2norm_tensors_kernel_and_its_backward(fcsa):
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 3, 77, 64, generator=g).to(torch.bfloat16)
+    dy = torch.randn(2, 3, 77, 64, generator=g).to(torch.bfloat16)
+    for groups in (1, 2, 8, 16):
+        xd = x.cuda().requires_grad_()
+        (y,) = fcsa.l2norm_tensors(xd, groups=groups)
+        y.backward(dy.cuda())
+        assert rel_err(y, oracle.l2norm(x.float().numpy(), groups)[0]) < 5e-3
+        # the kernel differentiates through the ROUNDED y it stored, like autograd on 16-bit tensors
+        assert rel_err(xd.grad, oracle.l2norm_backward(dy.float().numpy(), x.float().numpy(), groups)) < 2e-2
+
+
+def test_unsupported_inputs_still_correct(fcsa):
+    """float32 / attn_bias / other head dims have no fused kernel yet: they must still be right."""
+    g = torch.Generator().manual_seed(15)
+    q, k, v = (torch.randn(1, 2, 50, 32, generator=g) for _ in range(3))
+    with pytest.warns(UserWarning):
+        o = fcsa.flash_cosine_sim_attention(q.cuda(), k.cuda(), v.cuda(), causal=True)
+    assert rel_err(o, oracle.attention(q.numpy(), k.numpy(), v.numpy(), causal=True)) < 1e-4
+
+
+# ---- BASELINE.json configs ------------------------------------------------------------------------
+def test_config2_self_attn_1x8x1024x64_bf16_fwd(fcsa):
+    check(fcsa, (1, 8, 1024, 64), (1, 8, 1024, 64), torch.bfloat16, seed=2, grads=False)
+
+
+def test_config4_cross_attn_mask_single_head_kv_grouped(fcsa):
+    check(fcsa, (1, 8, 1024, 64), (1, 2048, 64), torch.bfloat16, seed=4, mask_p=0.25, groups=2)
+
+
+def _slice_check(fcsa, shape, dtype, slices, grads=True):
+    """Full-size run on the GPU; oracle on a few (batch, head) slices (each is an independent
+    attention problem, reference cu:1091-1092)."""
+    q, k, v, do, _ = make_inputs(shape, shape, dtype, seed=3)
+    grads = grads and shape[-1] in BWD_HEAD_DIMS
+    qd, kd, vd = (t.cuda().requires_grad_(grads) for t in (q, k, v))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, causal=True)
+    if grads:
+        o.backward(do.cuda())
+    for b, h in slices:
+        sl = lambda t: t[b:b + 1, h:h + 1].float().numpy()
+        ref = oracle.attention(sl(q), sl(k), sl(v), causal=True, d_out=sl(do) if grads else None)
+        ref = ref if grads else (ref,)
+        assert rel_err(o[b:b + 1, h:h + 1], ref[0]) <= TOL_OUT[dtype]
+        if grads:
+            for t, r in zip((qd, kd, vd), ref[1:]):
+                assert rel_err(t.grad[b:b + 1, h:h + 1], r) <= TOL_GRAD[dtype]
+    return qd, kd, vd, o
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_config3_causal_4x8x4096x64_fwd_bwd(fcsa, dtype):
+    qd, kd, vd, o = _slice_check(fcsa, (4, 8, 4096, 64), dtype, [(0, 0), (3, 7)])
+    # size-independent properties at full size
+    ones = torch.ones_like(vd)
+    o1 = fcsa.flash_cosine_sim_attention(qd.detach(), kd.detach(), ones, causal=True)
+    assert (o1.float() - 1).abs().max() < 1e-2             # rows are convex combinations of v
+    o2 = fcsa.flash_cosine_sim_attention(qd.detach(), kd.detach(), vd.detach(), causal=True)
+    assert torch.equal(o2, o.detach())                      # forward is deterministic
+    # causality: perturbing the last key/value must leave all earlier rows untouched
+    k2, v2 = kd.detach().clone(), vd.detach().clone()
+    k2[:, :, -1] += 1
+    v2[:, :, -1] += 1
+    o3 = fcsa.flash_cosine_sim_attention(qd.detach(), k2, v2, causal=True)
+    assert torch.equal(o3[:, :, :-1], o.detach()[:, :, :-1])
+
+
+def test_config5_long_context_slice_16384x128(fcsa):
+    """One rank's share of config 5 is (1, 16, 16384, 128); two heads checked against the oracle."""
+    _slice_check(fcsa, (1, 2, 16384, 128), torch.bfloat16, [(0, 1)], grads=True)
