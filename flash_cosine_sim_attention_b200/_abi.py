@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "fcsa_backward",
     "fcsa_l2norm_forward",
     "fcsa_l2norm_backward",
+    "fcsa_set_kernel_events",
 )
 
 
@@ -93,6 +94,8 @@ def load():
     lib.fcsa_l2norm_forward.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, c_void_p]
     lib.fcsa_l2norm_backward.restype = c_int32
     lib.fcsa_l2norm_backward.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, PT, c_void_p]
+    lib.fcsa_set_kernel_events.restype = c_int32
+    lib.fcsa_set_kernel_events.argtypes = [c_int32, c_void_p, c_void_p]
     _lib = lib
     return lib
 

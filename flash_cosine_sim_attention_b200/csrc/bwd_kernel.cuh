@@ -11,18 +11,22 @@
 //   1. bwd_prep_kernel    : per query row {c3 = log2(inv_l) - shift*log2e, delta} (fp32, never
 //                           rounded to 16 bit as the reference does at cu:1260/1820)
 //   2. fcsa_bwd_kernel    : one CTA per (key tile of 128, batch, head), key/value tile stationary
-//                           in shared memory, loop over 128-row query tiles.  Everything is computed
+//                           in shared memory, loop over query tiles of QT rows.  Everything is computed
 //                           TRANSPOSED (rows = keys): S^T = K Q^T and dP^T = V dO^T so that P^T and
 //                           dS^T land in TMEM exactly in the layout tcgen05 wants for an A operand
 //                           (dV += P^T dO, dK += dS^T Q read A from TMEM); dS is also staged in
-//                           shared memory (M-major) for dQ = dS K.  dQ partial tiles leave through
+//                           shared memory for the dQ product.  dQ partial tiles leave through
 //                           shared memory and a TMA bulk reduce-add into an fp32 accumulator -
 //                           no per-element global atomics (reference: cu:1602-1610).
 //   3. bwd_dq_finish_kernel: fp32 accumulator * scale -> 16-bit dq.
 //
-// TMEM columns (D = 64): S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448).
-// P^T / dS^T (packed 16-bit) overwrite the half of S^T / dP^T that the same warpgroup has just
-// read, so no extra columns and no cross-warpgroup hazards.
+// Two shapes of the same kernel (TMEM has 512 columns; dV and dK need D each):
+//   D = 64 : QT = 128.  S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448),
+//            dQ = dS K      (M = queries, A = dS from smem M-major, B = K)
+//   D = 128: QT = 64.   S^T [0,64)  dP^T [64,128)  dV [128,256) dK [256,384) dQ^T [384,448),
+//            dQ^T = K^T dS^T (M = features, A = K from smem M-major, B = dS^T)
+// P^T / dS^T (packed 16-bit) overwrite the part of S^T / dP^T that the same warpgroup has just
+// read, so they cost no columns and create no cross-warpgroup hazards.
 #pragma once
 
 #include "../../include/fcsa_b200.h"
@@ -31,22 +35,46 @@
 
 namespace fcsa {
 
+template <int D>
+struct BwdCfg {
+  static constexpr int QT = (D == 64) ? 128 : 64;        // query rows per tile
+  static constexpr int kKV = 128 * D * 2;                 // bytes of the K (or V) tile
+  static constexpr int kQ = QT * D * 2;                   // bytes of one Q (or dO) stage
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kOffK + kKV;
+  static constexpr int NST = 3;                           // Q / dO / stats ring depth
+  static constexpr int kOffQ = kOffV + kKV;
+  static constexpr int kOffDO = kOffQ + NST * kQ;
+  static constexpr int kDS = 128 * QT * 2;                // dS^T staging: 128 keys x QT queries, 16-bit
+  static constexpr int kOffDS = kOffDO + NST * kQ;
+  static constexpr int kOffDQ = kOffDS + kDS;             // fp32 staging 128 x 64 = 32 KB
+  static constexpr int kOffStats = kOffDQ + 32768;        // NST stages x 1 KB (2*QT floats used)
+  static constexpr int kOffBar = kOffStats + NST * 1024;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kThreads = 512;
+  // TMEM columns
+  static constexpr uint32_t TM_S = 0, TM_DP = QT, TM_DV = 2 * QT, TM_DK = 2 * QT + D, TM_DQ = 2 * QT + 2 * D;
+};
+
 // ------------------------------------------------------------------------------------------
 // workspace layout (all fp32):
-//   stats : [B*H][nqt][2][128]   c3 then delta for each 128-row query tile (padded rows = 0)
-//   dq_acc: [B*H][nqt][4 warps][D/4 chunks][32 rows][4]   (only what the dq finish kernel reads)
-//   dkv_acc (kv_heads == 1 only): dk [B][Nk][D] then dv [B][Nk][D]
+//   stats : [B*H][nqt][2][QT]      c3 then delta for each query tile (padded rows = 0)
+//   dq_acc: [B*H][nqt][4 warps][16 chunks][32 lanes][4]   32 KB per query tile, in the order the
+//           reduce warps produce it (D = 64: lane = query row, chunk = 4 features;
+//           D = 128: lane = feature, chunk = 4 query rows)
+//   dkv_acc (kv_heads == 1 < heads only): dk [B][Nk][D] then dv [B][Nk][D]
 // ------------------------------------------------------------------------------------------
 struct BwdWorkspace {
   size_t stats_off, dq_off, dkv_off, total;
-  int nqt;
+  int nqt, QT;
 };
 
 inline BwdWorkspace bwd_workspace_layout(int B, int H, int kv_heads, int Nq, int Nk, int D) {
   BwdWorkspace w;
-  w.nqt = (Nq + 127) / 128;
-  size_t stats = (size_t)B * H * w.nqt * 256 * 4;
-  size_t dq = (size_t)B * H * w.nqt * 128 * D * 4;
+  w.QT = (D == 64) ? 128 : 64;
+  w.nqt = (Nq + w.QT - 1) / w.QT;
+  size_t stats = (size_t)B * H * w.nqt * 2 * w.QT * 4;
+  size_t dq = (size_t)B * H * w.nqt * 32768;
   size_t dkv = (kv_heads == 1 && H > 1) ? (size_t)2 * B * Nk * D * 4 : 0;
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   w.stats_off = 0;
@@ -64,7 +92,7 @@ inline size_t bwd_workspace_bytes(int B, int H, int kv_heads, int Nq, int Nk, in
 // 1. preprocess
 // ------------------------------------------------------------------------------------------
 struct PrepArgs {
-  int B, H, Nq, D, nqt;
+  int B, H, Nq, D, nqt, QT;
   float c2;                         // shift * log2e
   const void* o;  long long o_sb, o_sh, o_sn;
   const void* d_o; long long do_sb, do_sh, do_sn;
@@ -79,7 +107,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
   const int rows_per_block = 256 / tpr;
   const long long prow = (long long)blockIdx.x * rows_per_block + threadIdx.x / tpr;  // padded row id
   const int tr = threadIdx.x % tpr;
-  const long long padded = (long long)a.nqt * 128;
+  const long long padded = (long long)a.nqt * a.QT;
   const long long total = (long long)a.B * a.H * padded;
   const bool in = prow < total;
   const long long pr = in ? prow : 0;
@@ -100,20 +128,20 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
   }
   for (int m = 1; m < tpr; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
   if (in && tr == 0) {
-    const int qt = row >> 7, r = row & 127;
-    float* st = a.stats + ((long long)bh * a.nqt + qt) * 256;
+    const int qt = row / a.QT, r = row % a.QT;
+    float* st = a.stats + ((long long)bh * a.nqt + qt) * 2 * a.QT;
     float c3 = 0.f, dl = 0.f;
     if (valid) {
       c3 = log2f(a.inv_l[(long long)bh * a.Nq + row]) - a.c2;
       dl = dot;
     }
     st[r] = c3;
-    st[128 + r] = dl;
+    st[a.QT + r] = dl;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// 2. main kernel (D = 64)
+// 2. main kernel
 // ------------------------------------------------------------------------------------------
 struct BwdArgs {
   int B, H, Nq, Nk, kv_heads, causal, has_mask, nqt;
@@ -127,29 +155,19 @@ struct BwdArgs {
   void* dv; long long dv_sb, dv_sh, dv_sn;
 };
 
-template <int D>
-struct BwdCfg {
-  static constexpr int kTile = 128 * D * 2;       // 16 KB at D = 64
-  static constexpr int kOffK = 0;
-  static constexpr int kOffV = kOffK + kTile;
-  static constexpr int kOffQ = kOffV + kTile;      // 2 stages
-  static constexpr int kOffDO = kOffQ + 2 * kTile; // 2 stages
-  static constexpr int kOffDS = kOffDO + 2 * kTile;   // 128 keys x 128 queries 16-bit = 32 KB
-  static constexpr int kOffDQ = kOffDS + 32768;       // fp32 staging 128 x D
-  static constexpr int kOffStats = kOffDQ + 128 * D * 4;  // 2 stages x 1 KB
-  static constexpr int kOffBar = kOffStats + 2048;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
-  static constexpr int kThreads = 512;
-};
-
 template <typename T, int D>
 __global__ void __launch_bounds__(512, 1)
 fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const BwdArgs a) {
-  static_assert(D == 64, "this kernel is the D = 64 variant");
+  static_assert(D == 64 || D == 128, "head dim 64 or 128");
   using Cfg = BwdCfg<D>;
-  constexpr int TILE = Cfg::kTile;
+  constexpr int QT = Cfg::QT;              // query rows per tile
+  constexpr int HALF = QT / 2;             // query columns each compute warpgroup owns
+  constexpr int KCH = D / 64;              // 64-feature chunks of every operand tile
+  constexpr int QCHUNK = QT * 128;         // bytes of one 64-feature chunk of a Q / dO stage
+  constexpr uint32_t TM_S = Cfg::TM_S, TM_DP = Cfg::TM_DP, TM_DV = Cfg::TM_DV, TM_DK = Cfg::TM_DK,
+                     TM_DQ = Cfg::TM_DQ;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -158,16 +176,16 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t sV = smem_u32(smem + Cfg::kOffV);
   const uint32_t sQ = smem_u32(smem + Cfg::kOffQ);
   const uint32_t sDO = smem_u32(smem + Cfg::kOffDO);
-  uint8_t* pDS = smem + Cfg::kOffDS;
-  const uint32_t sDS = smem_u32(pDS);
-  uint8_t* pDQ = smem + Cfg::kOffDQ;
-  const float* pStats = reinterpret_cast<const float*>(smem + Cfg::kOffStats);
+  const uint32_t sDS = smem_u32(smem + Cfg::kOffDS);
+  const uint32_t sDQ = smem_u32(smem + Cfg::kOffDQ);
+  const uint32_t sStats = smem_u32(smem + Cfg::kOffStats);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int NST = Cfg::NST;
   enum {
-    KV_FULL = 0, Q_FULL = 1, Q_EMPTY = 3, DO_FULL = 5, DO_EMPTY = 7, S_FULL = 9, P_FULL = 10,
-    DP_FULL = 11, DS_FULL = 12, DS_FREE = 13, DQ_FULL = 14, DQ_EMPTY = 15, DKV_FULL = 16, NBARS = 17
+    KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
+    S_FULL = DO_EMPTY + NST, P_FULL, DP_FULL, DS_FULL, DS_FREE, DQ_FULL, DQ_EMPTY, DKV_FULL, NBARS
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
@@ -184,8 +202,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int key0 = jt * 128;
   int i_lo = 0;
   if (a.causal) {
-    const int x = key0 - off - 127;                     // first query row that can see key0 ... (tile granularity)
-    i_lo = x <= 0 ? 0 : (x + 127) >> 7;
+    // first query tile with a row that can see key0: QT*i + QT-1 + off >= key0
+    const int x = key0 - off - (QT - 1);
+    i_lo = x <= 0 ? 0 : (x + QT - 1) / QT;
   }
   const int NI = a.nqt - i_lo;                          // number of query tiles to visit (>= 1)
 
@@ -196,7 +215,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
     mbar_init(BAR(KV_FULL), 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(BAR(Q_FULL + s), 1);
       mbar_init(BAR(Q_EMPTY + s), 1);
       mbar_init(BAR(DO_FULL + s), 1);
@@ -220,43 +239,75 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
   if (wg == 3) {
     reg_dealloc<64>();
+#ifdef FCSA_TRACE
+    if (warp == 14 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
+      // passive observer: when do the tensor-pipe results become visible?  (bounded spins: an
+      // observer that falls two phases behind must not hang the kernel)
+      auto watch = [&](int bar, uint32_t par) {
+        for (int tries = 0; tries < (1 << 22); ++tries)
+          if (mbar_try_wait(BAR(bar), par)) return;
+      };
+      for (int i = 0; i < NI; ++i) {
+        watch(S_FULL, i & 1);
+        FCSA_TR(5, i, 0);
+        watch(DP_FULL, i & 1);
+        FCSA_TR(5, i, 1);
+        watch(DQ_FULL, i & 1);
+        FCSA_TR(5, i, 2);
+      }
+    }
+#endif
     if (warp == 12) {
       // =============================== TMA producer ===============================
       if (NI > 0 && elect_one()) {
-        mbar_expect_tx(BAR(KV_FULL), 2 * TILE);
-        tma_load_4d(sK, &tm_k, BAR(KV_FULL), 0, key0, hk, b);
-        tma_load_4d(sV, &tm_v, BAR(KV_FULL), 0, key0, hk, b);
+        mbar_expect_tx(BAR(KV_FULL), 2 * Cfg::kKV);
+#pragma unroll
+        for (int ch = 0; ch < KCH; ++ch) {
+          tma_load_4d(sK + ch * 16384, &tm_k, BAR(KV_FULL), ch * 64, key0, hk, b);
+          tma_load_4d(sV + ch * 16384, &tm_v, BAR(KV_FULL), ch * 64, key0, hk, b);
+        }
         for (int i = 0; i < NI; ++i) {
-          const int st = i & 1, qt = i_lo + i;
-          const uint32_t par = ((i >> 1) & 1) ^ 1;
+          const int st = i % NST, qt = i_lo + i;
+          const uint32_t par = ((i / NST) & 1) ^ 1;
           mbar_wait(BAR(Q_EMPTY + st), par);
-          mbar_expect_tx(BAR(Q_FULL + st), TILE + 1024);
-          tma_load_4d(sQ + st * TILE, &tm_q, BAR(Q_FULL + st), 0, qt * 128, h, b);
-          bulk_load_1d(smem_u32(smem + Cfg::kOffStats) + st * 1024,
-                       a.stats + ((long long)bh * a.nqt + qt) * 256, 1024, BAR(Q_FULL + st));
+          FCSA_TR(4, i, 0);
+          mbar_expect_tx(BAR(Q_FULL + st), Cfg::kQ + 8 * QT);
+#pragma unroll
+          for (int ch = 0; ch < KCH; ++ch)
+            tma_load_4d(sQ + st * Cfg::kQ + ch * QCHUNK, &tm_q, BAR(Q_FULL + st), ch * 64, qt * QT, h, b);
+          bulk_load_1d(sStats + st * 1024,
+                       a.stats + ((long long)bh * a.nqt + qt) * 2 * QT, 8 * QT, BAR(Q_FULL + st));
           mbar_wait(BAR(DO_EMPTY + st), par);
-          mbar_expect_tx(BAR(DO_FULL + st), TILE);
-          tma_load_4d(sDO + st * TILE, &tm_do, BAR(DO_FULL + st), 0, qt * 128, h, b);
+          FCSA_TR(4, i, 1);
+          mbar_expect_tx(BAR(DO_FULL + st), Cfg::kQ);
+#pragma unroll
+          for (int ch = 0; ch < KCH; ++ch)
+            tma_load_4d(sDO + st * Cfg::kQ + ch * QCHUNK, &tm_do, BAR(DO_FULL + st), ch * 64, qt * QT, h, b);
         }
       }
     } else if (warp == 13) {
       // =============================== MMA issuer =================================
       if (NI > 0 && elect_one()) {
-        constexpr uint32_t idesc_s = umma_idesc<T>(128, 128, 0, 0);   // S^T, dP^T
+        constexpr uint32_t idesc_s = umma_idesc<T>(128, QT, 0, 0);    // S^T, dP^T  (A, B K-major)
         constexpr uint32_t idesc_ts = umma_idesc<T>(128, D, 0, 1);    // dV, dK (A from TMEM, B MN-major)
-        constexpr uint32_t idesc_dq = umma_idesc<T>(128, D, 1, 1);    // dQ (A, B MN-major)
+        constexpr uint32_t idesc_dq = umma_idesc<T>(128, 64, 1, 1);   // dQ / dQ^T (A, B MN-major)
+        // S^T = K Q^T (and dP^T = V dO^T): contraction over the D features, 16 per instruction
         auto issue_ST = [&](uint32_t d_col, uint32_t a_smem, uint32_t b_smem) {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)
-            umma_ss(tmem + d_col, umma_desc_sw128(a_smem + k * 32, 16, 1024),
-                    umma_desc_sw128(b_smem + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_ss(tmem + d_col,
+                    umma_desc_sw128(a_smem + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
         };
-        // A operand halves written by compute warpgroup 0 (queries 0..63) and 1 (64..127)
-        auto a_col = [](uint32_t base, int kk) { return base + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8); };
+        // packed A operand written by compute warpgroup 0 (queries [0,HALF)) and 1 ([HALF,QT)):
+        // 16 queries = 8 columns per k-step, each warpgroup's block starts at its own S^T columns
+        auto a_col = [](uint32_t base, int kk) {
+          return base + (kk < HALF / 16 ? kk * 8 : HALF + (kk - HALF / 16) * 8);
+        };
 
         mbar_wait(BAR(KV_FULL), 0);
         mbar_wait(BAR(Q_FULL + 0), 0);
@@ -269,49 +320,59 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         umma_commit(BAR(DP_FULL));
 
         for (int i = 0; i < NI; ++i) {
-          const int st = i & 1;
+          const int st = i % NST, sn = (i + 1) % NST;
+          const uint32_t parn = ((i + 1) / NST) & 1;
           const bool more = (i + 1 < NI);
           // ---- dV += P^T dO ----
+          FCSA_TR(0, i, 0);
           mbar_wait(BAR(P_FULL), i & 1);
+          FCSA_TR(0, i, 1);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
+          for (int kk = 0; kk < QT / 16; ++kk)
             umma_ts(tmem + TM_DV, tmem + a_col(TM_S, kk),
-                    umma_desc_sw128(sDO + st * TILE + kk * 2048, 16384, 1024), idesc_ts,
+                    umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
                     (i > 0 || kk > 0) ? 1u : 0u);
           umma_commit(BAR(DO_EMPTY + st));
           // ---- S^T(i+1) ----
           if (more) {
-            mbar_wait(BAR(Q_FULL + (st ^ 1)), ((i + 1) >> 1) & 1);
+            mbar_wait(BAR(Q_FULL + sn), parn);
             tc_fence_after();
-            issue_ST(TM_S, sK, sQ + (st ^ 1) * TILE);
+            issue_ST(TM_S, sK, sQ + sn * Cfg::kQ);
             umma_commit(BAR(S_FULL));
           }
           // ---- dK += dS^T Q ----
+          FCSA_TR(0, i, 2);
           mbar_wait(BAR(DS_FULL), i & 1);
+          FCSA_TR(0, i, 3);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
+          for (int kk = 0; kk < QT / 16; ++kk)
             umma_ts(tmem + TM_DK, tmem + a_col(TM_DP, kk),
-                    umma_desc_sw128(sQ + st * TILE + kk * 2048, 16384, 1024), idesc_ts,
+                    umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
                     (i > 0 || kk > 0) ? 1u : 0u);
           umma_commit(BAR(Q_EMPTY + st));
-          // ---- dQ = dS K ----
+          // ---- dQ = dS K  (D = 64)   or   dQ^T = K^T dS^T  (D = 128) : contraction over the 128 keys ----
           mbar_wait(BAR(DQ_EMPTY), (i & 1) ^ 1);
+          FCSA_TR(0, i, 4);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tmem + TM_DQ, umma_desc_sw128(sDS + kk * 2048, 16384, 1024),
-                    umma_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t d_ds = umma_desc_sw128(sDS + kk * 2048, 16384, 1024);
+            const uint64_t d_k = umma_desc_sw128(sK + kk * 2048, 16384, 1024);
+            if (D == 64) umma_ss(tmem + TM_DQ, d_ds, d_k, idesc_dq, kk > 0 ? 1u : 0u);
+            else umma_ss(tmem + TM_DQ, d_k, d_ds, idesc_dq, kk > 0 ? 1u : 0u);
+          }
           umma_commit(BAR(DQ_FULL));
           umma_commit(BAR(DS_FREE));
           // ---- dP^T(i+1) ----
           if (more) {
-            mbar_wait(BAR(DO_FULL + (st ^ 1)), ((i + 1) >> 1) & 1);
+            mbar_wait(BAR(DO_FULL + sn), parn);
             tc_fence_after();
-            issue_ST(TM_DP, sV, sDO + (st ^ 1) * TILE);
+            issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
             umma_commit(BAR(DP_FULL));
           }
+          FCSA_TR(0, i, 5);
         }
         umma_commit(BAR(DKV_FULL));
       }
@@ -321,10 +382,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     reg_dealloc<96>();
     const int wq = warp & 3;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    uint8_t* my_stage = pDQ + wq * (32 * D * 4);                // 8 KB per warp
+    const uint32_t my_stage = sDQ + wq * 8192;                  // 8 KB per warp
     for (int i = 0; i < NI; ++i) {
       const int qt = i_lo + i;
       mbar_wait(BAR(DQ_FULL), i & 1);
+      if (warp == 8 && lane == 0) FCSA_TR(3, i, 0);
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld_x32(lane_base + TM_DQ, r0);
@@ -333,89 +395,88 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       mbar_arrive(BAR(DQ_EMPTY));
       // the previous bulk reduce must have finished reading the staging buffer
+      if (warp == 8 && lane == 0) FCSA_TR(3, i, 1);
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
+      if (warp == 8 && lane == 0) FCSA_TR(3, i, 2);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(my_stage + c * 512 + lane * 16) =
-            make_uint4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
+        sts128(my_stage + c * 512 + lane * 16, r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(my_stage + (8 + c) * 512 + lane * 16) =
-            make_uint4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
+        sts128(my_stage + (8 + c) * 512 + lane * 16, r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        float* dst = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * (32 * D);
-        bulk_reduce_add_f32(dst, smem_u32(my_stage), 32 * D * 4);
+        float* dst = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048;
+        bulk_reduce_add_f32(dst, my_stage, 8192);
         bulk_commit_group();
       }
+      if (warp == 8 && lane == 0) FCSA_TR(3, i, 3);
     }
     if (lane == 0) bulk_wait_group<0>();
     __syncwarp();
   } else {
     // =============================== compute warpgroups =============================
     reg_alloc<176>();
-    const int w = wg;                        // 0: queries [0,64) of each tile, 1: [64,128)
+    const int w = wg;                        // 0: queries [0,HALF) of each tile, 1: [HALF,QT)
     const int wq = warp & 3;
     const int r = wq * 32 + lane;            // key row inside the tile
     const int key_g = key0 + r;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t tS = lane_base + TM_S + 64 * w;
-    const uint32_t tDP = lane_base + TM_DP + 64 * w;
+    const uint32_t tS = lane_base + TM_S + HALF * w;
+    const uint32_t tDP = lane_base + TM_DP + HALF * w;
     const float c1 = a.c1;
     bool key_ok = key_g < a.Nk;
     if (a.has_mask && key_ok) key_ok = a.mask[(long long)b * a.mask_sb + key_g] != 0;
     const bool tile_key_ragged = (key0 + 127 >= a.Nk) || a.has_mask;
 
     for (int i = 0; i < NI; ++i) {
-      const int st = i & 1, qt = i_lo + i;
-      const int row0 = qt * 128;
-      const float* c3p = pStats + st * 256 + 64 * w;
-      const float* dlp = c3p + 128;
+      const int st = i % NST, qt = i_lo + i;
+      const int row0 = qt * QT;
+      const uint32_t c3a = sStats + st * 1024 + (HALF * w) * 4;   // c3 of this warpgroup's queries
+      const uint32_t dla = c3a + QT * 4;                           // delta
       // visible iff lo <= cc <= hi  (cc = query index inside the tile)
-      const bool need_mask = tile_key_ragged || (row0 + 127 >= a.Nq) ||
+      const bool need_mask = tile_key_ragged || (row0 + QT - 1 >= a.Nq) ||
                              (a.causal && (key0 + 127 > row0 + off));
-      int lo = 0, hi = 127;
+      int lo = 0, hi = QT - 1;
       if (need_mask) {
-        hi = min(127, a.Nq - 1 - row0);
+        hi = min(QT - 1, a.Nq - 1 - row0);
         if (a.causal) lo = max(0, key_g - off - row0);
         if (!key_ok) lo = 1000;
       }
 
-      mbar_wait(BAR(Q_FULL + st), (i >> 1) & 1);     // stats for this tile are in smem
+      const bool tr_lane = (wq == 0 && lane == 0);
+      if (tr_lane) FCSA_TR(1 + w, i, 0);
+      mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // stats for this tile are in smem
       mbar_wait(BAR(S_FULL), i & 1);
+      if (tr_lane) FCSA_TR(1 + w, i, 1);
       tc_fence_after();
-      float p[64];
-      {
-        uint32_t s0[32], s1[32];
-        tmem_ld_x32(tS, s0);
-        tmem_ld_x32(tS + 32, s1);
+      float p[HALF];
+#pragma unroll
+      for (int hh = 0; hh < HALF / 32; ++hh) {
+        uint32_t s[32];
+        tmem_ld_x32(tS + 32 * hh, s);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float4 k0 = *reinterpret_cast<const float4*>(c3p + c);
-          const float4 k1 = *reinterpret_cast<const float4*>(c3p + 32 + c);
-          p[c + 0] = ex2_approx(fmaf(__uint_as_float(s0[c + 0]), c1, k0.x));
-          p[c + 1] = ex2_approx(fmaf(__uint_as_float(s0[c + 1]), c1, k0.y));
-          p[c + 2] = ex2_approx(fmaf(__uint_as_float(s0[c + 2]), c1, k0.z));
-          p[c + 3] = ex2_approx(fmaf(__uint_as_float(s0[c + 3]), c1, k0.w));
-          p[32 + c + 0] = ex2_approx(fmaf(__uint_as_float(s1[c + 0]), c1, k1.x));
-          p[32 + c + 1] = ex2_approx(fmaf(__uint_as_float(s1[c + 1]), c1, k1.y));
-          p[32 + c + 2] = ex2_approx(fmaf(__uint_as_float(s1[c + 2]), c1, k1.z));
-          p[32 + c + 3] = ex2_approx(fmaf(__uint_as_float(s1[c + 3]), c1, k1.w));
+          const float4 k0 = lds128f(c3a + (32 * hh + c) * 4);
+          p[32 * hh + c + 0] = ex2_approx(fmaf(__uint_as_float(s[c + 0]), c1, k0.x));
+          p[32 * hh + c + 1] = ex2_approx(fmaf(__uint_as_float(s[c + 1]), c1, k0.y));
+          p[32 * hh + c + 2] = ex2_approx(fmaf(__uint_as_float(s[c + 2]), c1, k0.z));
+          p[32 * hh + c + 3] = ex2_approx(fmaf(__uint_as_float(s[c + 3]), c1, k0.w));
         }
       }
       if (need_mask) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const int cc = 64 * w + c;
+        for (int c = 0; c < HALF; ++c) {
+          const int cc = HALF * w + c;
           p[c] = (cc >= lo && cc <= hi) ? p[c] : 0.f;
         }
       }
       // P^T -> TMEM (packed), over the S^T columns this warpgroup has just consumed
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = 0; hh < HALF / 32; ++hh) {
         uint32_t pk[16];
 #pragma unroll
         for (int q2 = 0; q2 < 16; ++q2) pk[q2] = pack2<T>(p[32 * hh + 2 * q2], p[32 * hh + 2 * q2 + 1]);
@@ -424,20 +485,23 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL));
+      if (tr_lane) FCSA_TR(1 + w, i, 2);
 
       // ---- dS = P * (dP - delta) ----
       mbar_wait(BAR(DP_FULL), i & 1);
+      if (tr_lane) FCSA_TR(1 + w, i, 3);
       tc_fence_after();
-      mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);          // dQ(i-1) has finished reading the smem dS
+      mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);          // the dQ product of tile i-1 has finished reading smem dS
+      if (tr_lane) FCSA_TR(1 + w, i, 4);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = 0; hh < HALF / 32; ++hh) {
         uint32_t d[32];
         tmem_ld_x32(tDP + 32 * hh, d);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float4 dl = *reinterpret_cast<const float4*>(dlp + 32 * hh + c);
+          const float4 dl = lds128f(dla + (32 * hh + c) * 4);
           const float d0 = p[32 * hh + c + 0] * (__uint_as_float(d[c + 0]) - dl.x);
           const float d1 = p[32 * hh + c + 1] * (__uint_as_float(d[c + 1]) - dl.y);
           const float d2 = p[32 * hh + c + 2] * (__uint_as_float(d[c + 2]) - dl.z);
@@ -446,16 +510,18 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           pk[c / 2 + 1] = pack2<T>(d2, d3);
         }
         tmem_st_x16(tDP + 16 * hh, pk);
-        // the same 32 queries -> shared memory, row = key, M(query)-contiguous, 128B swizzle
+        // the same 32 queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
+        const int q0 = HALF * w + 32 * hh;            // first query of this group inside the tile
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(pDS + w * 16384 + sw128_offset(r, 4 * hh + q4)) =
-              make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), pk[4 * q4],
+                 pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       }
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(DS_FULL));
+      if (tr_lane) FCSA_TR(1 + w, i, 5);
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
@@ -516,20 +582,20 @@ struct DqFinishArgs {
   void* dq; long long sb, sh, sn;
 };
 
-// one thread = 8 consecutive features of one row
+// D = 64: accumulator tile = [4 warps][16 feature-chunks][32 rows][4 features].
+// One thread = 8 consecutive features of one row.
 template <typename T>
-__global__ void __launch_bounds__(256) bwd_dq_finish_kernel(const DqFinishArgs a) {
-  const int tpr = a.D >> 3;
+__global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs a) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)a.B * a.H * a.Nq * tpr;
+  const long long total = (long long)a.B * a.H * a.Nq * 8;
   if (idx >= total) return;
-  const int c8 = (int)(idx % tpr);
-  const long long rowid = idx / tpr;
+  const int c8 = (int)(idx & 7);
+  const long long rowid = idx >> 3;
   const int row = (int)(rowid % a.Nq);
   const int bh = (int)(rowid / a.Nq);
   const int b = bh / a.H, h = bh % a.H;
   const int qt = row >> 7, r = row & 127, wq = r >> 5, rl = r & 31;
-  const float* tile = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * (32 * a.D);
+  const float* tile = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048;
   const float4 lo = *reinterpret_cast<const float4*>(tile + (2 * c8) * 128 + rl * 4);
   const float4 hi = *reinterpret_cast<const float4*>(tile + (2 * c8 + 1) * 128 + rl * 4);
   uint4 o4;
@@ -539,6 +605,41 @@ __global__ void __launch_bounds__(256) bwd_dq_finish_kernel(const DqFinishArgs a
   o4.w = pack2<T>(hi.z * a.scale, hi.w * a.scale);
   T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
   *reinterpret_cast<uint4*>(dst) = o4;
+}
+
+// D = 128: accumulator tile (64 query rows) = [4 warps][16 row-chunks][32 features][4 rows], i.e.
+// transposed.  One block = one tile: coalesced float4 loads -> shared memory -> row-major stores.
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArgs a) {
+  __shared__ float tile[64][129];
+  const long long unit = blockIdx.x;                       // (bh, qt)
+  const int qt = (int)(unit % a.nqt);
+  const int bh = (int)(unit / a.nqt);
+  const int b = bh / a.H, h = bh % a.H;
+  const float* src = a.dq_acc + unit * 8192;
+  for (int f = threadIdx.x; f < 2048; f += 256) {         // 2048 float4 per tile
+    const float4 v = *reinterpret_cast<const float4*>(src + f * 4);
+    const int wq = f >> 9, c = (f >> 5) & 15, ln = f & 31;
+    const int d = wq * 32 + ln, r0 = c * 4;
+    tile[r0 + 0][d] = v.x;
+    tile[r0 + 1][d] = v.y;
+    tile[r0 + 2][d] = v.z;
+    tile[r0 + 3][d] = v.w;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {      // 16 x 8 features per row
+    const int rr = e >> 4, c8 = e & 15;
+    const int row = qt * 64 + rr;
+    if (row >= a.Nq) continue;
+    const float* s = &tile[rr][c8 * 8];
+    uint4 o4;
+    o4.x = pack2<T>(s[0] * a.scale, s[1] * a.scale);
+    o4.y = pack2<T>(s[2] * a.scale, s[3] * a.scale);
+    o4.z = pack2<T>(s[4] * a.scale, s[5] * a.scale);
+    o4.w = pack2<T>(s[6] * a.scale, s[7] * a.scale);
+    T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
+    *reinterpret_cast<uint4*>(dst) = o4;
+  }
 }
 
 struct KvFinishArgs {
@@ -579,11 +680,13 @@ struct BwdHostArgs {
   fcsa_tensor q, k, v, o, d_o, dq, dk, dv;
   const float* inv_l;
   void* workspace;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // optional: recorded around the main kernel
 };
 
 template <typename T, int D>
 int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, const char** err,
                    cudaError_t* ce) {
+  using Cfg = BwdCfg<D>;
   const BwdWorkspace w = bwd_workspace_layout(h.B, h.H, h.kv_heads, h.Nq, h.Nk, D);
   uint8_t* ws = reinterpret_cast<uint8_t*>(h.workspace);
   float* stats = reinterpret_cast<float*>(ws + w.stats_off);
@@ -594,19 +697,19 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
   cudaError_t e;
 
   // zero the fp32 accumulators (dq, and dk/dv when shared across heads)
-  e = cudaMemsetAsync(dq_acc, 0, w.dkv_off - w.dq_off + (shared_kv ? (size_t)2 * h.B * h.Nk * D * 4 : 0), stream);
+  e = cudaMemsetAsync(dq_acc, 0, w.total - w.dq_off, stream);
   if (e != cudaSuccess) { *err = "cudaMemsetAsync(workspace)"; *ce = e; return FCSA_ERR_CUDA; }
 
   // 1. preprocess
   {
     PrepArgs pa;
-    pa.B = h.B; pa.H = h.H; pa.Nq = h.Nq; pa.D = D; pa.nqt = w.nqt;
+    pa.B = h.B; pa.H = h.H; pa.Nq = h.Nq; pa.D = D; pa.nqt = w.nqt; pa.QT = Cfg::QT;
     pa.c2 = h.shift * log2e;
     pa.o = h.o.ptr; pa.o_sb = h.o.sb; pa.o_sh = h.o.sh; pa.o_sn = h.o.sn;
     pa.d_o = h.d_o.ptr; pa.do_sb = h.d_o.sb; pa.do_sh = h.d_o.sh; pa.do_sn = h.d_o.sn;
     pa.inv_l = h.inv_l; pa.stats = stats;
     const int rows_per_block = 256 / (D / 8);
-    const long long rows = (long long)h.B * h.H * w.nqt * 128;
+    const long long rows = (long long)h.B * h.H * w.nqt * Cfg::QT;
     const long long grid = (rows + rows_per_block - 1) / rows_per_block;
     bwd_prep_kernel<T><<<(unsigned)grid, 256, 0, stream>>>(pa);
     e = cudaGetLastError();
@@ -616,10 +719,10 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
   // 2. main
   {
     CUtensorMap tq, tk, tv, tdo;
-    if (make_tensor_map_bhnd(&tq, h.q.ptr, h.dtype_bf16, h.B, h.H, h.Nq, D, h.q.sb, h.q.sh, h.q.sn, 128) ||
+    if (make_tensor_map_bhnd(&tq, h.q.ptr, h.dtype_bf16, h.B, h.H, h.Nq, D, h.q.sb, h.q.sh, h.q.sn, Cfg::QT) ||
         make_tensor_map_bhnd(&tk, h.k.ptr, h.dtype_bf16, h.B, h.kv_heads, h.Nk, D, h.k.sb, h.k.sh, h.k.sn, 128) ||
         make_tensor_map_bhnd(&tv, h.v.ptr, h.dtype_bf16, h.B, h.kv_heads, h.Nk, D, h.v.sb, h.v.sh, h.v.sn, 128) ||
-        make_tensor_map_bhnd(&tdo, h.d_o.ptr, h.dtype_bf16, h.B, h.H, h.Nq, D, h.d_o.sb, h.d_o.sh, h.d_o.sn, 128)) {
+        make_tensor_map_bhnd(&tdo, h.d_o.ptr, h.dtype_bf16, h.B, h.H, h.Nq, D, h.d_o.sb, h.d_o.sh, h.d_o.sn, Cfg::QT)) {
       *err = "cuTensorMapEncodeTiled failed (backward)";
       return FCSA_ERR_INVALID;
     }
@@ -632,7 +735,6 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     a.dk_acc = dkv_acc; a.dv_acc = dkv_acc + (size_t)h.B * h.Nk * D;
     a.dk = h.dk.ptr; a.dk_sb = h.dk.sb; a.dk_sh = h.dk.sh; a.dk_sn = h.dk.sn;
     a.dv = h.dv.ptr; a.dv_sb = h.dv.sb; a.dv_sh = h.dv.sh; a.dv_sn = h.dv.sn;
-    using Cfg = BwdCfg<D>;
     auto kern = fcsa_bwd_kernel<T, D>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -641,8 +743,10 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
       attr_set = true;
     }
     const long long grid = (long long)((h.Nk + 127) / 128) * h.B * h.H;
+    if (h.ev_start) cudaEventRecord(h.ev_start, stream);
     kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(tq, tk, tv, tdo, a);
     e = cudaGetLastError();
+    if (h.ev_stop) cudaEventRecord(h.ev_stop, stream);
     if (e != cudaSuccess) { *err = "backward kernel launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
   }
@@ -651,8 +755,12 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     DqFinishArgs fa;
     fa.B = h.B; fa.H = h.H; fa.Nq = h.Nq; fa.D = D; fa.nqt = w.nqt; fa.scale = h.scale;
     fa.dq_acc = dq_acc; fa.dq = h.dq.ptr; fa.sb = h.dq.sb; fa.sh = h.dq.sh; fa.sn = h.dq.sn;
-    const long long total = (long long)h.B * h.H * h.Nq * (D / 8);
-    bwd_dq_finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fa);
+    if (D == 64) {
+      const long long total = (long long)h.B * h.H * h.Nq * 8;
+      bwd_dq_finish64_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fa);
+    } else {
+      bwd_dq_finish128_kernel<T><<<(unsigned)((long long)h.B * h.H * w.nqt), 256, 0, stream>>>(fa);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
@@ -676,12 +784,12 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
 
 inline int run_backward(const BwdHostArgs& h, cudaStream_t stream, int* launches, const char** err,
                         cudaError_t* ce) {
-  if (h.D != 64) {
-    *err = "backward: head_dim 128 kernel not built yet (64 only)";
-    return FCSA_ERR_UNSUPPORTED;
+  if (h.D == 64) {
+    if (h.dtype_bf16) return run_backward_t<__nv_bfloat16, 64>(h, stream, launches, err, ce);
+    return run_backward_t<__half, 64>(h, stream, launches, err, ce);
   }
-  if (h.dtype_bf16) return run_backward_t<__nv_bfloat16, 64>(h, stream, launches, err, ce);
-  return run_backward_t<__half, 64>(h, stream, launches, err, ce);
+  if (h.dtype_bf16) return run_backward_t<__nv_bfloat16, 128>(h, stream, launches, err, ce);
+  return run_backward_t<__half, 128>(h, stream, launches, err, ce);
 }
 
 }  // namespace fcsa

@@ -23,6 +23,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -110,8 +111,10 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
   }
   const long long grid = (long long)a.n_qblk * p->batch * p->heads;
   if (grid > 0x7FFFFFFFLL) return fail(FCSA_ERR_INVALID, "problem too large for one launch");
+  if (g_ev[0][0]) cudaEventRecord(g_ev[0][0], stream);
   kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(tq, tk, tv, a);
   cudaError_t e = cudaGetLastError();
+  if (g_ev[0][1]) cudaEventRecord(g_ev[0][1], stream);
   if (e != cudaSuccess) return cuda_fail(e, "forward kernel launch");
   g_launches.fetch_add(1);
   return FCSA_OK;
@@ -164,6 +167,13 @@ const char* fcsa_last_error(void) { return g_err; }
 
 int64_t fcsa_debug(void) { return g_launches.load(); }
 
+int fcsa_set_kernel_events(int32_t which, void* start_event, void* stop_event) {
+  if (which != 0 && which != 1) return fail(FCSA_ERR_INVALID, "which must be 0 (forward) or 1 (backward)");
+  g_ev[which][0] = reinterpret_cast<cudaEvent_t>(start_event);
+  g_ev[which][1] = reinterpret_cast<cudaEvent_t>(stop_event);
+  return FCSA_OK;
+}
+
 int fcsa_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
                  const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, void* stream) {
   int r;
@@ -211,6 +221,8 @@ int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor
   h.q = *q; h.k = *k; h.v = *v; h.o = *o; h.d_o = *d_o; h.dq = *dq; h.dk = *dk; h.dv = *dv;
   h.inv_l = inv_l;
   h.workspace = workspace;
+  h.ev_start = g_ev[1][0];
+  h.ev_stop = g_ev[1][1];
   int launches = 0;
   const char* err = nullptr;
   cudaError_t ce = cudaSuccess;

@@ -10,9 +10,13 @@
 //   * warp 9   : tcgen05 issuer (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with P_t read from TMEM)
 //   * warps 0-3: "softmax" warpgroup for tile 0, warps 4-7 for tile 1: thread == query row,
 //                tcgen05.ld S -> exp2(fma) -> row sum in a register -> 16-bit P -> tcgen05.st
-//   * TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D); P_t aliases the
-//     upper half of S_t (64 columns of packed 16-bit pairs).  Because there is no row max
-//     there is no rescaling of O: the accumulator never leaves TMEM until the epilogue.
+//   * TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).  Because there is
+//     no row max there is no rescaling of O: the accumulator never leaves TMEM until the epilogue.
+//     D = 64 : P0 [384,448) P1 [448,512) (packed 16-bit pairs) are separate columns, so the
+//              softmax warpgroup hands S_t back as soon as it sits in registers and S_t(j+1)
+//              is computed while the exps of tile j are still running;
+//     D = 128: no spare columns - P_t overwrites the upper half of S_t and S_t(j+1) is issued
+//              behind P_t(j) V_j in the (in-order) tensor pipe.
 #pragma once
 
 #include "sm100_primitives.cuh"
@@ -67,7 +71,8 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS,
                 V_EMPTY = V_FULL + VS, S_FULL = V_EMPTY + VS, P_FULL = S_FULL + 2,
-                O_FULL = P_FULL + 2, NBARS = O_FULL + 2;
+                O_FULL = P_FULL + 2, S_FREE = O_FULL + 2, P_FREE = S_FREE + 2, NBARS = P_FREE + 2;
+  constexpr bool PSEP = (D == 64);     // P in its own TMEM columns (see header comment)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,6 +121,8 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(BAR(S_FULL + t), 1);
       mbar_init(BAR(P_FULL + t), 128);
       mbar_init(BAR(O_FULL + t), 1);
+      mbar_init(BAR(S_FREE + t), 128);
+      mbar_init(BAR(P_FREE + t), 1);
     }
     fence_mbar_init();
   }
@@ -181,24 +188,44 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
       for (int j = 0; j < NT; ++j) {
         const int vs = j % VS;
+        if (PSEP) {
+          // next S tiles first: they only need the softmax warpgroup to have pulled S(j) into registers
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j + 1 < n_t[t]) {
+              mbar_wait(BAR(S_FREE + t), j & 1);
+              FCSA_TR(0, j, t);
+              tc_fence_after();
+              issue_S(t, j + 1);
+            }
+          }
+          if (j + 1 < NT) umma_commit(BAR(K_EMPTY + (j + 1) % KS));
+        }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (j < n_t[t]) {
             mbar_wait(BAR(P_FULL + t), j & 1);
+            FCSA_TR(0, j, 2 + 2 * t);
             mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
+            FCSA_TR(0, j, 3 + 2 * t);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              umma_ts(tmem + 256 + t * D, tmem + t * 128 + 64 + k * 8,
+              umma_ts(tmem + 256 + t * D, tmem + (PSEP ? 384 + t * 64 : t * 128 + 64) + k * 8,
                       umma_desc_sw128(sV + vs * TILE + k * 2048, 16384, 1024), idesc_o,
                       (j > 0 || k > 0) ? 1u : 0u);
             }
-            if (j + 1 < n_t[t]) issue_S(t, j + 1);
-            else umma_commit(BAR(O_FULL + t));
+            if (PSEP) {
+              umma_commit(BAR(P_FREE + t));
+              if (j + 1 >= n_t[t]) umma_commit(BAR(O_FULL + t));
+            } else {
+              if (j + 1 < n_t[t]) issue_S(t, j + 1);
+              else umma_commit(BAR(O_FULL + t));
+            }
           }
         }
         umma_commit(BAR(V_EMPTY + vs));
-        if (j + 1 < NT) umma_commit(BAR(K_EMPTY + (j + 1) % KS));
+        if (!PSEP && j + 1 < NT) umma_commit(BAR(K_EMPTY + (j + 1) % KS));
       }
     }
   } else {
@@ -209,14 +236,17 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int row_g = m0 + 128 * t + r;      // global query row
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t tS = lane_base + t * 128;
-    const uint32_t tP = tS + 64;
+    const uint32_t tP = PSEP ? lane_base + 384 + t * 64 : tS + 64;
     const uint32_t tO = lane_base + 256 + t * D;
     const int nt = n_t[t];
     const float c1 = a.c1, nc2 = -a.c2;
     float l = 0.f;
 
+    const bool tr_lane = (wq == 0 && lane == 0);
     for (int j = 0; j < nt; ++j) {
+      if (tr_lane) FCSA_TR(1 + t, j, 0);
       mbar_wait(BAR(S_FULL + t), j & 1);
+      if (tr_lane) FCSA_TR(1 + t, j, 1);
       tc_fence_after();
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_x32(tS + 0, s0);
@@ -224,6 +254,17 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld_x32(tS + 64, s2);
       tmem_ld_x32(tS + 96, s3);
       tmem_ld_wait();
+      if (tr_lane) FCSA_TR(1 + t, j, 2);
+      if (PSEP) {
+        tc_fence_before();
+        mbar_arrive(BAR(S_FREE + t));                       // S_t may be overwritten by tile j+1 now
+      }
+      // before the first store of P(j): P_t(j-1) V must have finished reading the P columns.  Waited
+      // for as late as possible - after the first chunk of exps - so it never costs anything.
+      auto p_cols_free = [&]() {
+        if (PSEP && j > 0) mbar_wait(BAR(P_FREE + t), (j - 1) & 1);
+      };
+      if (tr_lane) FCSA_TR(1 + t, j, 3);
 
       const int col0 = j * 128;
       const bool need_mask = a.has_mask || (col0 + 127 >= a.Nk) ||
@@ -238,6 +279,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             l += p0 + p1;
             pk[i] = pack2<T>(p0, p1);
           }
+          if (c == 0) p_cols_free();
           tmem_st_x16(tP + c * 16, pk);
         };
         chunk(s0, 0);
@@ -271,6 +313,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             l += p0 + p1;
             pk[i] = pack2<T>(p0, p1);
           }
+          if (c == 0) p_cols_free();
           tmem_st_x16(tP + c * 16, pk);
         };
         chunk(s0, 0);
@@ -278,9 +321,11 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         chunk(s2, 2);
         chunk(s3, 3);
       }
+      if (tr_lane) FCSA_TR(1 + t, j, 4);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
+      if (tr_lane) FCSA_TR(1 + t, j, 5);
     }
 
     // ---- epilogue: O * 1/max(l, eps) -> global ----------------------------------------

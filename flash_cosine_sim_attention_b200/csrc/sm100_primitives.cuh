@@ -14,6 +14,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Optional in-kernel timeline (tests/cuda/trace_*.cu build with -DFCSA_TRACE): one lane per role
+// of one CTA stamps clock64() at pipeline events.  Compiled out of the product library.
+#ifdef FCSA_TRACE
+#ifndef FCSA_TRACE_CTA
+#define FCSA_TRACE_CTA 0
+#endif
+__device__ long long g_fcsa_trace[8][48][8];
+#define FCSA_TR(role, it, slot)                                                       \
+  do {                                                                                \
+    if (blockIdx.x == FCSA_TRACE_CTA && (it) < 48) g_fcsa_trace[role][it][slot] = clock64(); \
+  } while (0)
+#else
+#define FCSA_TR(role, it, slot) do { } while (0)
+#endif
+
 namespace fcsa {
 
 // ----------------------------------------------------------------------------------
@@ -74,6 +89,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (UMMA/TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// explicit shared-state-space accesses (a generic pointer makes ptxas emit LD.E / ST.E, which
+// go through address translation and cost extra wavefronts on broadcast reads)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
 }
 
 // named barrier among a subset of the CTA's warps

@@ -125,6 +125,16 @@ int fcsa_l2norm_backward(int32_t dtype, int32_t batch, int32_t heads, int32_t ro
                          const fcsa_tensor* y, const float* rnorm, const fcsa_tensor* dx,
                          void* stream);
 
+/*
+ * Measurement hook (bench.py roofline line; no reference counterpart - the reference only timed
+ * whole calls, flash_cosine_sim_attention/benchmark.py:7-58).  While set, fcsa_forward (which = 0)
+ * or fcsa_backward (which = 1) records the cudaEvent_t `start` / `stop` on the launch stream
+ * immediately before / after its dominant kernel (the tcgen05 attention kernel, not the
+ * pre/post passes).  Pass NULL, NULL to clear.  State is process-wide (autograd calls the
+ * backward from its own thread), so use it from single-stream measurement code only.
+ */
+int fcsa_set_kernel_events(int32_t which, void* start_event, void* stop_event);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+// In-kernel timeline of one CTA of the backward kernel at the benchmark shape (4,8,4096,64) causal.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DFCSA_TRACE -o trace_bwd trace_bwd.cu
+// Test infrastructure only.
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../../flash_cosine_sim_attention_b200/csrc/bwd_kernel.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
+
+__global__ void fill(__nv_bfloat16* p, size_t n, unsigned seed, float amp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned x = (unsigned)i * 2654435761u + seed;
+  x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+  p[i] = __float2bfloat16(((x & 0xFFFF) / 65536.0f - 0.5f) * amp);
+}
+__global__ void fillf(float* p, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int main(int argc, char** argv) {
+  const int B = 4, H = 8, N = 4096, D = 64;
+  const size_t n = (size_t)B * H * N * D;
+  __nv_bfloat16 *q, *k, *v, *o, *d_o, *dq, *dk, *dv;
+  float* inv_l;
+  for (auto pp : {&q, &k, &v, &o, &d_o, &dq, &dk, &dv}) CK(cudaMalloc(pp, n * 2));
+  CK(cudaMalloc(&inv_l, (size_t)B * H * N * 4));
+  fill<<<(n + 255) / 256, 256>>>(q, n, 1, 0.25f);     // |q.k| small: p ~ exp(-8)...; timing only
+  fill<<<(n + 255) / 256, 256>>>(k, n, 2, 0.25f);
+  fill<<<(n + 255) / 256, 256>>>(v, n, 3, 2.f);
+  fill<<<(n + 255) / 256, 256>>>(o, n, 4, 1.f);
+  fill<<<(n + 255) / 256, 256>>>(d_o, n, 5, 2.f);
+  fillf<<<((size_t)B * H * N + 255) / 256, 256>>>(inv_l, (size_t)B * H * N, 1.0f);
+  size_t wsb = fcsa::bwd_workspace_bytes(B, H, H, N, N, D);
+  void* ws;
+  CK(cudaMalloc(&ws, wsb));
+  fcsa::BwdHostArgs h;
+  h.dtype_bf16 = true; h.B = B; h.H = H; h.kv_heads = H; h.Nq = N; h.Nk = N; h.D = D; h.causal = 1;
+  h.scale = 8.f; h.shift = 8.f; h.mask = nullptr; h.mask_sb = 0;
+  auto T = [&](void* p) { fcsa_tensor t; t.ptr = p; t.sb = (long long)H * N * D; t.sh = (long long)N * D; t.sn = D; return t; };
+  h.q = T(q); h.k = T(k); h.v = T(v); h.o = T(o); h.d_o = T(d_o); h.dq = T(dq); h.dk = T(dk); h.dv = T(dv);
+  h.inv_l = inv_l; h.workspace = ws;
+  int launches = 0; const char* err = nullptr; cudaError_t ce = cudaSuccess;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  h.ev_start = e0; h.ev_stop = e1;
+  for (int rep = 0; rep < 3; ++rep) {
+    int r = fcsa::run_backward(h, 0, &launches, &err, &ce);
+    if (r) { printf("run_backward failed %d %s\n", r, err ? err : ""); return 1; }
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("rep %d: main kernel %.1f us\n", rep, ms * 1e3);
+  }
+  static long long tr[8][48][8];
+  CK(cudaMemcpyFromSymbol(tr, g_fcsa_trace, sizeof(tr)));
+  long long t0 = tr[0][0][0];
+  const char* names[6] = {"MMA  [pre-Pwait, P_FULL seen, pre-DSwait, DS_FULL seen, DQ_EMPTY seen, iter issued]",
+                          "CMP0 [start, S_FULL seen, P arrived, DP_FULL seen, DS_FREE seen, DS arrived]",
+                          "CMP1 [same]", "RED  [DQ_FULL seen, ld done, stage free, reduce issued]",
+                          "TMA  [Q_EMPTY seen, DO_EMPTY seen]", "OBS  [S_FULL, DP_FULL, DQ_FULL complete]"};
+  int nslots[6] = {6, 6, 6, 4, 2, 3};
+  for (int role = 0; role < 6; ++role) {
+    printf("--- %s\n", names[role]);
+    for (int i = 0; i < 12; ++i) {
+      printf("  it %2d:", i);
+      for (int s = 0; s < nslots[role]; ++s) printf(" %8lld", tr[role][i][s] ? tr[role][i][s] - t0 : -1);
+      printf("\n");
+    }
+  }
+  // iteration period from the MMA role
+  printf("MMA iteration period (cycles):");
+  for (int i = 1; i < 32; ++i) printf(" %lld", tr[0][i][1] - tr[0][i - 1][1]);
+  printf("\n");
+  return 0;
+}

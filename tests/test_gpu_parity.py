@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_OUT = {torch.bfloat16: 1e-2, torch.float16: 2e-3}
 TOL_GRAD = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
-BWD_HEAD_DIMS = (64,)
+BWD_HEAD_DIMS = (64, 128)
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +37,12 @@ def fcsa():
 def rel_err(got, ref):
     got = got.detach().float().cpu().numpy().astype(np.float64)
     assert np.isfinite(got).all(), "NaN/Inf in CUDA result"
-    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
+    mag = np.abs(ref).max()
+    if mag < 1e-6:
+        # the exact answer is identically zero (e.g. dq with a single key: softmax over one
+        # element): only 16-bit rounding noise may remain, judged on an absolute scale
+        return np.abs(got).max() / 5.0
+    return np.abs(got - ref).max() / mag
 
 
 def make_inputs(qs, kvs, dtype, seed, mask_p=None, amp=1.0):
@@ -101,11 +106,18 @@ def test_reference_golden_vectors(fcsa, path):
     q, k, v = (torch.from_numpy(z[n]).to(dt).cuda().requires_grad_(grads) for n in ("q", "k", "v"))
     assert np.array_equal(q.detach().float().cpu().numpy(), z["q"])
     o = fcsa.flash_cosine_sim_attention(q, k, v, mask=mask, **kw)
-    assert rel_err(o, z["o"]) <= TOL_OUT[dt]
+    want = {n: z[n] for n in ("o", "dq", "dk", "dv")}
+    if kw.get("causal") and z["q"].shape[-2] > z["k"].shape[-2]:
+        # queries that see no key: the naive reference averages v, the fused kernels (reference's
+        # included, cu:1239) give 0.  Compare with the oracle's "zero" variant, which test_oracle.py
+        # pins to these same golden vectors in its "mean" variant.
+        ref = oracle.attention(z["q"], z["k"], z["v"], d_out=z["d_out"], empty_rows="zero", **kw)
+        want = dict(zip(("o", "dq", "dk", "dv"), ref))
+    assert rel_err(o, want["o"]) <= TOL_OUT[dt]
     if grads:
         o.backward(torch.from_numpy(z["d_out"]).to(dt).cuda())
         for name, t in (("dq", q), ("dk", k), ("dv", v)):
-            assert rel_err(t.grad, z[name]) <= TOL_GRAD[dt], name
+            assert rel_err(t.grad, want[name]) <= TOL_GRAD[dt], name
 
 
 # ---- features the reference never tested (SURVEY.md par. 4) ----------------------------------------
