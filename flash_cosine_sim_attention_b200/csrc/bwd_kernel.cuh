@@ -21,13 +21,16 @@
 //   3. bwd_dq_finish_kernel: fp32 accumulator * scale -> 16-bit dq.
 //
 // Two shapes of the same kernel (TMEM has 512 columns; dV and dK need D each):
-//   D = 64 : QT = 128.  S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448),
+//   D = 64 : QT = 128.  S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448) X [448,512)
 //            dQ = dS K      (M = queries, A = dS from smem M-major, B = K)
-//   D = 128: QT = 64.   S^T [0,64)  dP^T [64,128)  dV [128,256) dK [256,384) dQ^T [384,448),
+//   D = 128: QT = 64.   S^T [0,64)  dP^T [64,128)  dV [128,256) dK [256,384) dQ^T [384,448) X [448,480)
 //            dQ^T = K^T dS^T (M = features, A = K from smem M-major, B = dS^T)
-// P^T / dS^T (packed 16-bit) overwrite the part of S^T / dP^T that the same warpgroup has just
-// read, so they cost no columns and create no cross-warpgroup hazards.
+// X holds P^T (packed 16 bit), the TMEM A operand of dV; dS^T (the A operand of dK) is written
+// over the dP^T columns its producer has already consumed.  The two compute warpgroups form a
+// two-stage pipeline (exp stage on the MUFU pipe for tile i+1, dS stage on the FMA pipe for tile i).
 #pragma once
+
+#include <type_traits>
 
 #include "../../include/fcsa_b200.h"
 #include "sm100_primitives.cuh"
@@ -53,7 +56,8 @@ struct BwdCfg {
   static constexpr int kSmem = kOffBar + 256 + 1024;
   static constexpr int kThreads = 512;
   // TMEM columns
-  static constexpr uint32_t TM_S = 0, TM_DP = QT, TM_DV = 2 * QT, TM_DK = 2 * QT + D, TM_DQ = 2 * QT + 2 * D;
+  static constexpr uint32_t TM_S = 0, TM_DP = QT, TM_DV = 2 * QT, TM_DK = 2 * QT + D, TM_DQ = 2 * QT + 2 * D,
+                            TM_X = 2 * QT + 2 * D + 64;   // QT/2 columns of packed P^T, then dS^T
 };
 
 // ------------------------------------------------------------------------------------------
@@ -163,11 +167,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   static_assert(D == 64 || D == 128, "head dim 64 or 128");
   using Cfg = BwdCfg<D>;
   constexpr int QT = Cfg::QT;              // query rows per tile
-  constexpr int HALF = QT / 2;             // query columns each compute warpgroup owns
   constexpr int KCH = D / 64;              // 64-feature chunks of every operand tile
   constexpr int QCHUNK = QT * 128;         // bytes of one 64-feature chunk of a Q / dO stage
+  constexpr int NST = Cfg::NST;
   constexpr uint32_t TM_S = Cfg::TM_S, TM_DP = Cfg::TM_DP, TM_DV = Cfg::TM_DV, TM_DK = Cfg::TM_DK,
-                     TM_DQ = Cfg::TM_DQ;
+                     TM_DQ = Cfg::TM_DQ, TM_X = Cfg::TM_X;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -182,10 +186,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int NST = Cfg::NST;
   enum {
     KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
-    S_FULL = DO_EMPTY + NST, P_FULL, DP_FULL, DS_FULL, DS_FREE, DQ_FULL, DQ_EMPTY, DKV_FULL, NBARS
+    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, P_READ, PV_DONE, DP_FULL, DS_FULL, DS_FREE,
+    DQ_FULL, DQ_EMPTY, DKV_FULL, NBARS
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
@@ -222,9 +226,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(BAR(DO_EMPTY + s), 1);
     }
     mbar_init(BAR(S_FULL), 1);
-    mbar_init(BAR(P_FULL), 256);
+    mbar_init(BAR(S_FREE), 128);
+    mbar_init(BAR(P_FULL), 128);
+    mbar_init(BAR(P_READ), 128);
+    mbar_init(BAR(PV_DONE), 1);
     mbar_init(BAR(DP_FULL), 1);
-    mbar_init(BAR(DS_FULL), 256);
+    mbar_init(BAR(DS_FULL), 128);
     mbar_init(BAR(DS_FREE), 1);
     mbar_init(BAR(DQ_FULL), 1);
     mbar_init(BAR(DQ_EMPTY), 128);
@@ -241,13 +248,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
 
   if (wg == 3) {
-    reg_dealloc<64>();
+    reg_dealloc<72>();
 #ifdef FCSA_TRACE
     if (warp == 14 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
       // passive observer: when do the tensor-pipe results become visible?  (bounded spins: an
       // observer that falls two phases behind must not hang the kernel)
       auto watch = [&](int bar, uint32_t par) {
-        for (int tries = 0; tries < (1 << 22); ++tries)
+        for (int tries = 0; tries < (1 << 14); ++tries)
           if (mbar_try_wait(BAR(bar), par)) return;
       };
       for (int i = 0; i < NI; ++i) {
@@ -255,8 +262,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         FCSA_TR(5, i, 0);
         watch(DP_FULL, i & 1);
         FCSA_TR(5, i, 1);
-        watch(DQ_FULL, i & 1);
+        watch(PV_DONE, i & 1);
         FCSA_TR(5, i, 2);
+        watch(DQ_FULL, i & 1);
+        FCSA_TR(5, i, 3);
       }
     }
 #endif
@@ -290,6 +299,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     } else if (warp == 13) {
       // =============================== MMA issuer =================================
+      // Issue order per query tile i (it follows the order in which the inputs become ready, so the
+      // blocking waits never hold back work that could run):
+      //   S^T(i+1)   as soon as the exp warpgroup holds S^T(i) in registers
+      //   dV(i)      when P^T(i) is in the X columns
+      //   dK(i), dP^T(i+1), dQ(i)   when dS^T(i) is in TMEM / shared memory (dS^T aliases dP^T,
+      //              so dP^T(i+1) goes behind dK(i) in the in-order tensor pipe)
       if (NI > 0 && elect_one()) {
         constexpr uint32_t idesc_s = umma_idesc<T>(128, QT, 0, 0);    // S^T, dP^T  (A, B K-major)
         constexpr uint32_t idesc_ts = umma_idesc<T>(128, D, 0, 1);    // dV, dK (A from TMEM, B MN-major)
@@ -303,12 +318,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         };
-        // packed A operand written by compute warpgroup 0 (queries [0,HALF)) and 1 ([HALF,QT)):
-        // 16 queries = 8 columns per k-step, each warpgroup's block starts at its own S^T columns
-        auto a_col = [](uint32_t base, int kk) {
-          return base + (kk < HALF / 16 ? kk * 8 : HALF + (kk - HALF / 16) * 8);
-        };
-
         mbar_wait(BAR(KV_FULL), 0);
         mbar_wait(BAR(Q_FULL + 0), 0);
         tc_fence_after();
@@ -323,38 +332,46 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const int st = i % NST, sn = (i + 1) % NST;
           const uint32_t parn = ((i + 1) / NST) & 1;
           const bool more = (i + 1 < NI);
-          // ---- dV += P^T dO ----
-          FCSA_TR(0, i, 0);
-          mbar_wait(BAR(P_FULL), i & 1);
-          FCSA_TR(0, i, 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < QT / 16; ++kk)
-            umma_ts(tmem + TM_DV, tmem + a_col(TM_S, kk),
-                    umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
-                    (i > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(BAR(DO_EMPTY + st));
           // ---- S^T(i+1) ----
           if (more) {
+            mbar_wait(BAR(S_FREE), i & 1);
             mbar_wait(BAR(Q_FULL + sn), parn);
             tc_fence_after();
             issue_ST(TM_S, sK, sQ + sn * Cfg::kQ);
             umma_commit(BAR(S_FULL));
+            FCSA_TR(0, i, 0);
           }
-          // ---- dK += dS^T Q ----
-          FCSA_TR(0, i, 2);
-          mbar_wait(BAR(DS_FULL), i & 1);
-          FCSA_TR(0, i, 3);
+          // ---- dV += P^T dO ----
+          mbar_wait(BAR(P_FULL), i & 1);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < QT / 16; ++kk)
-            umma_ts(tmem + TM_DK, tmem + a_col(TM_DP, kk),
+            umma_ts(tmem + TM_DV, tmem + TM_X + kk * 8,
+                    umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
+                    (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(BAR(PV_DONE));
+          umma_commit(BAR(DO_EMPTY + st));
+          FCSA_TR(0, i, 1);
+          // ---- dK += dS^T Q ----
+          mbar_wait(BAR(DS_FULL), i & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < QT / 16; ++kk)
+            umma_ts(tmem + TM_DK, tmem + TM_DP + kk * 8,
                     umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
                     (i > 0 || kk > 0) ? 1u : 0u);
           umma_commit(BAR(Q_EMPTY + st));
-          // ---- dQ = dS K  (D = 64)   or   dQ^T = K^T dS^T  (D = 128) : contraction over the 128 keys ----
+          FCSA_TR(0, i, 2);
+          // ---- dP^T(i+1) (overwrites dS^T(i): behind dK(i) in the pipe) ----
+          if (more) {
+            mbar_wait(BAR(DO_FULL + sn), parn);
+            tc_fence_after();
+            issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
+            umma_commit(BAR(DP_FULL));
+            FCSA_TR(0, i, 3);
+          }
+          // ---- dQ = dS K (D = 64) or dQ^T = K^T dS^T (D = 128): contraction over the 128 keys ----
           mbar_wait(BAR(DQ_EMPTY), (i & 1) ^ 1);
-          FCSA_TR(0, i, 4);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -365,21 +382,14 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           umma_commit(BAR(DQ_FULL));
           umma_commit(BAR(DS_FREE));
-          // ---- dP^T(i+1) ----
-          if (more) {
-            mbar_wait(BAR(DO_FULL + sn), parn);
-            tc_fence_after();
-            issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
-            umma_commit(BAR(DP_FULL));
-          }
-          FCSA_TR(0, i, 5);
+          FCSA_TR(0, i, 4);
         }
         umma_commit(BAR(DKV_FULL));
       }
     }
   } else if (wg == 2) {
     // =============================== dQ reduce warpgroup ============================
-    reg_dealloc<96>();
+    reg_dealloc<88>();
     const int wq = warp & 3;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t my_stage = sDQ + wq * 8192;                  // 8 KB per warp
@@ -395,10 +405,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       mbar_arrive(BAR(DQ_EMPTY));
       // the previous bulk reduce must have finished reading the staging buffer
-      if (warp == 8 && lane == 0) FCSA_TR(3, i, 1);
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
-      if (warp == 8 && lane == 0) FCSA_TR(3, i, 2);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         sts128(my_stage + c * 512 + lane * 16, r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
@@ -412,119 +420,170 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         bulk_reduce_add_f32(dst, my_stage, 8192);
         bulk_commit_group();
       }
-      if (warp == 8 && lane == 0) FCSA_TR(3, i, 3);
+      if (warp == 8 && lane == 0) FCSA_TR(3, i, 1);
     }
     if (lane == 0) bulk_wait_group<0>();
     __syncwarp();
   } else {
     // =============================== compute warpgroups =============================
-    reg_alloc<176>();
-    const int w = wg;                        // 0: queries [0,HALF) of each tile, 1: [HALF,QT)
+    // Two-stage software pipeline over the query tiles, one stage per warpgroup, so that the
+    // MUFU-bound stage (exp) of tile i+1 overlaps the FMA-bound stage (dS) of tile i:
+    //   warpgroup 0: S^T -> P^T = exp2(S^T*c1 + c3)            -> X columns (packed 16 bit)
+    //   warpgroup 1: dP^T, P^T -> dS^T = P^T * (dP^T - delta)  -> over the dP^T columns it has
+    //                already consumed (packed 16 bit) and to shared memory
+    // Thread = key row.
     const int wq = warp & 3;
     const int r = wq * 32 + lane;            // key row inside the tile
     const int key_g = key0 + r;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t tS = lane_base + TM_S + HALF * w;
-    const uint32_t tDP = lane_base + TM_DP + HALF * w;
-    const float c1 = a.c1;
-    bool key_ok = key_g < a.Nk;
-    if (a.has_mask && key_ok) key_ok = a.mask[(long long)b * a.mask_sb + key_g] != 0;
-    const bool tile_key_ragged = (key0 + 127 >= a.Nk) || a.has_mask;
+    const uint32_t tX = lane_base + TM_X;
+    const bool tr_lane = (wq == 0 && lane == 0);
 
-    for (int i = 0; i < NI; ++i) {
-      const int st = i % NST, qt = i_lo + i;
-      const int row0 = qt * QT;
-      const uint32_t c3a = sStats + st * 1024 + (HALF * w) * 4;   // c3 of this warpgroup's queries
-      const uint32_t dla = c3a + QT * 4;                           // delta
-      // visible iff lo <= cc <= hi  (cc = query index inside the tile)
-      const bool need_mask = tile_key_ragged || (row0 + QT - 1 >= a.Nq) ||
-                             (a.causal && (key0 + 127 > row0 + off));
-      int lo = 0, hi = QT - 1;
-      if (need_mask) {
-        hi = min(QT - 1, a.Nq - 1 - row0);
-        if (a.causal) lo = max(0, key_g - off - row0);
-        if (!key_ok) lo = 1000;
-      }
+    if (wg == 0) {
+      reg_alloc<200>();
+      const uint32_t tS = lane_base + TM_S;
+      const float c1 = a.c1;
+      bool key_ok = key_g < a.Nk;
+      if (a.has_mask && key_ok) key_ok = a.mask[(long long)b * a.mask_sb + key_g] != 0;
+      const bool tile_key_ragged = (key0 + 127 >= a.Nk) || a.has_mask;
 
-      const bool tr_lane = (wq == 0 && lane == 0);
-      if (tr_lane) FCSA_TR(1 + w, i, 0);
-      mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // stats for this tile are in smem
-      mbar_wait(BAR(S_FULL), i & 1);
-      if (tr_lane) FCSA_TR(1 + w, i, 1);
-      tc_fence_after();
-      float p[HALF];
-#pragma unroll
-      for (int hh = 0; hh < HALF / 32; ++hh) {
-        uint32_t s[32];
-        tmem_ld_x32(tS + 32 * hh, s);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 k0 = lds128f(c3a + (32 * hh + c) * 4);
-          p[32 * hh + c + 0] = ex2_approx(fmaf(__uint_as_float(s[c + 0]), c1, k0.x));
-          p[32 * hh + c + 1] = ex2_approx(fmaf(__uint_as_float(s[c + 1]), c1, k0.y));
-          p[32 * hh + c + 2] = ex2_approx(fmaf(__uint_as_float(s[c + 2]), c1, k0.z));
-          p[32 * hh + c + 3] = ex2_approx(fmaf(__uint_as_float(s[c + 3]), c1, k0.w));
+      for (int i = 0; i < NI; ++i) {
+        const int st = i % NST, qt = i_lo + i;
+        const int row0 = qt * QT;
+        const uint32_t c3a = sStats + st * 1024;
+        // visible iff lo <= cc <= hi  (cc = query index inside the tile)
+        const bool need_mask = tile_key_ragged || (row0 + QT - 1 >= a.Nq) ||
+                               (a.causal && (key0 + 127 > row0 + off));
+        int lo = 0, hi = QT - 1;
+        if (need_mask) {
+          hi = min(QT - 1, a.Nq - 1 - row0);
+          if (a.causal) lo = max(0, key_g - off - row0);
+          if (!key_ok) lo = 1000;
         }
-      }
-      if (need_mask) {
+        if (tr_lane) FCSA_TR(1, i, 0);
+        mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // c3 of this tile is in smem
+        mbar_wait(BAR(S_FULL), i & 1);
+        if (tr_lane) FCSA_TR(1, i, 1);
+        tc_fence_after();
+        // Chunks of 32 query columns, the TMEM load of chunk c+1 in flight under the math of
+        // chunk c.  All shared-memory operands of a chunk are fetched in one batch first so the
+        // exp chain (FFMA -> MUFU -> pack) of 32 independent elements can be pipelined freely.
+        // The masked variant is a separate instantiation: a per-element `if (need_mask)` compiles
+        // to a taken branch per element pair and starves the warp of instructions.
+        constexpr int NC = QT / 32;
+        uint32_t pk[NC][16];
+        auto exp_tile = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
+          uint32_t s[2][32];
+          tmem_ld_x32(tS, s[0]);
 #pragma unroll
-        for (int c = 0; c < HALF; ++c) {
-          const int cc = HALF * w + c;
-          p[c] = (cc >= lo && cc <= hi) ? p[c] : 0.f;
+          for (int c = 0; c < NC; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NC) {
+              tmem_ld_x32(tS + 32 * (c + 1), s[(c + 1) & 1]);
+            } else {
+              tc_fence_before();
+              mbar_arrive(BAR(S_FREE));                   // S^T(i+1) may be produced now
+              if (tr_lane) FCSA_TR(1, i, 2);
+            }
+            float c3v[32];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 k0 = lds128f(c3a + (32 * c + e) * 4);
+              c3v[e] = k0.x; c3v[e + 1] = k0.y; c3v[e + 2] = k0.z; c3v[e + 3] = k0.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(s[c & 1][e]), c1, c3v[e]));
+              float p1 = ex2_approx(fmaf(__uint_as_float(s[c & 1][e + 1]), c1, c3v[e + 1]));
+              if (MASKED) {
+                const int cc = 32 * c + e;
+                p0 = (cc >= lo && cc <= hi) ? p0 : 0.f;
+                p1 = (cc + 1 >= lo && cc + 1 <= hi) ? p1 : 0.f;
+              }
+              pk[c][e / 2] = pack2<T>(p0, p1);
+            }
+          }
+        };
+        if (need_mask) exp_tile(std::true_type{});
+        else exp_tile(std::false_type{});
+        if (tr_lane) FCSA_TR(1, i, 3);
+        // X still holds P^T(i-1): dV(i-1) and the dS warpgroup must be done reading it
+        if (i > 0) {
+          mbar_wait(BAR(PV_DONE), (i - 1) & 1);
+          mbar_wait(BAR(P_READ), (i - 1) & 1);
         }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_st_x16(tX + 16 * c, pk[c]);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(BAR(P_FULL));
+        if (tr_lane) FCSA_TR(1, i, 4);
       }
-      // P^T -> TMEM (packed), over the S^T columns this warpgroup has just consumed
+    } else {
+      reg_alloc<152>();
+      const uint32_t tDP = lane_base + TM_DP;
+      for (int i = 0; i < NI; ++i) {
+        const int st = i % NST;
+        const uint32_t dla = sStats + st * 1024 + QT * 4;       // delta of this tile's queries
+        if (tr_lane) FCSA_TR(2, i, 0);
+        mbar_wait(BAR(P_FULL), i & 1);
+        if (tr_lane) FCSA_TR(2, i, 1);
+        mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);
+        mbar_wait(BAR(DP_FULL), i & 1);
+        if (tr_lane) FCSA_TR(2, i, 2);
+        tc_fence_after();
+        constexpr int NC = QT / 32;
+        uint32_t d[2][32], pp[2][16];
+        tmem_ld_x32(tDP, d[0]);
+        tmem_ld_x16(tX, pp[0]);
 #pragma unroll
-      for (int hh = 0; hh < HALF / 32; ++hh) {
-        uint32_t pk[16];
+        for (int c = 0; c < NC; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < NC) {                                // prefetch the next chunk
+            tmem_ld_x32(tDP + 32 * (c + 1), d[(c + 1) & 1]);
+            tmem_ld_x16(tX + 16 * (c + 1), pp[(c + 1) & 1]);
+          } else {
+            tc_fence_before();
+            mbar_arrive(BAR(P_READ));                      // X may take P^T(i+1) (once dV(i) is done too)
+          }
+          float dlv[32];
 #pragma unroll
-        for (int q2 = 0; q2 < 16; ++q2) pk[q2] = pack2<T>(p[32 * hh + 2 * q2], p[32 * hh + 2 * q2 + 1]);
-        tmem_st_x16(tS + 16 * hh, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(BAR(P_FULL));
-      if (tr_lane) FCSA_TR(1 + w, i, 2);
-
-      // ---- dS = P * (dP - delta) ----
-      mbar_wait(BAR(DP_FULL), i & 1);
-      if (tr_lane) FCSA_TR(1 + w, i, 3);
-      tc_fence_after();
-      mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);          // the dQ product of tile i-1 has finished reading smem dS
-      if (tr_lane) FCSA_TR(1 + w, i, 4);
+          for (int e = 0; e < 32; e += 4) {
+            const float4 dl = lds128f(dla + (32 * c + e) * 4);
+            dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
+          }
+          uint32_t pk[16];
 #pragma unroll
-      for (int hh = 0; hh < HALF / 32; ++hh) {
-        uint32_t d[32];
-        tmem_ld_x32(tDP + 32 * hh, d);
-        tmem_ld_wait();
-        uint32_t pk[16];
+          for (int e = 0; e < 32; e += 2) {
+            const float2 pa = unpack2<T>(pp[c & 1][e / 2]);
+            const float d0 = pa.x * (__uint_as_float(d[c & 1][e]) - dlv[e]);
+            const float d1 = pa.y * (__uint_as_float(d[c & 1][e + 1]) - dlv[e + 1]);
+            pk[e / 2] = pack2<T>(d0, d1);
+          }
+          if (c == 0) {
+            mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);        // the dQ product of tile i-1 has left smem dS
+            if (tr_lane) FCSA_TR(2, i, 3);
+          }
+          // packed dS^T over dP^T columns [16c, 16c+16) - all inside chunks this thread has loaded
+          tmem_st_x16(tDP + 16 * c, pk);
+          // the same 32 queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
+          const int q0 = 32 * c;
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 dl = lds128f(dla + (32 * hh + c) * 4);
-          const float d0 = p[32 * hh + c + 0] * (__uint_as_float(d[c + 0]) - dl.x);
-          const float d1 = p[32 * hh + c + 1] * (__uint_as_float(d[c + 1]) - dl.y);
-          const float d2 = p[32 * hh + c + 2] * (__uint_as_float(d[c + 2]) - dl.z);
-          const float d3 = p[32 * hh + c + 3] * (__uint_as_float(d[c + 3]) - dl.w);
-          pk[c / 2] = pack2<T>(d0, d1);
-          pk[c / 2 + 1] = pack2<T>(d2, d3);
+          for (int q4 = 0; q4 < 4; ++q4)
+            sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), pk[4 * q4],
+                   pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
         }
-        tmem_st_x16(tDP + 16 * hh, pk);
-        // the same 32 queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
-        const int q0 = HALF * w + 32 * hh;            // first query of this group inside the tile
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), pk[4 * q4],
-                 pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(BAR(DS_FULL));
+        if (tr_lane) FCSA_TR(2, i, 4);
       }
-      tmem_st_wait();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(BAR(DS_FULL));
-      if (tr_lane) FCSA_TR(1 + w, i, 5);
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
+    const int w = wg;
     if (NI > 0) {
       mbar_wait(BAR(DKV_FULL), 0);
       tc_fence_after();

@@ -216,7 +216,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
 
-__global__ void __launch_bounds__(256) probe_exp(float* out, int iters, int mode, long long* cycles) {
+__global__ void __launch_bounds__(512) probe_exp(float* out, int iters, int mode, long long* cycles) {
   float a[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = -0.001f * (threadIdx.x + 1) - 0.01f * i;
@@ -238,6 +238,111 @@ __global__ void __launch_bounds__(256) probe_exp(float* out, int iters, int mode
   for (int i = 0; i < 8; ++i) s += a[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+// ------------------------------------------------------------------------------------
+// TMEM -> register bandwidth (tcgen05.ld 32x32b.x32), no tensor-pipe activity
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) probe_ldtm(float* out, int iters, int with_exp, long long* cycles) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  float acc = 0.f;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(lane_base + ((c * 32 + (warp >> 2) * 128) & 511), r);
+      tmem_ld_wait();
+      if (with_exp) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += ex2_approx(__uint_as_float(r[i]) * 1e-30f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += __uint_as_float(r[i] & 1u);
+      }
+    }
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------
+// tcgen05.ld latency while the tensor pipe streams MMAs (accumulator traffic in TMEM)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1) probe_ldtm_mma(float* out, int iters, int mma_mode, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  __shared__ uint32_t slot;
+  __shared__ volatile int stop_flag;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) stop_flag = 0;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp < 4) {
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float acc = 0.f;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(lane_base + c * 32, r);      // columns [0,128): not written by the MMAs below
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += __uint_as_float(r[i] & 1u);
+      }
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = acc;
+    if (threadIdx.x == 0) { *cycles = t1 - t0; stop_flag = 1; }
+  } else if (warp == 4 && mma_mode) {
+    if (elect_one()) {
+      const uint32_t sA = smem_u32(smem), sB = sA + 32768;
+      // mode 1: SS M128 N128 into columns [256,384); mode 2: TS M128 N64 (A from tmem [384..]) into [256,320)
+      const uint32_t idesc = mma_mode == 1 ? umma_idesc<bf16>(128, 128, 0, 0) : umma_idesc<bf16>(128, 64, 0, 1);
+      int n = 0;
+      while (!stop_flag && n < (1 << 20)) {
+        for (int k = 0; k < 8; ++k) {
+          if (mma_mode == 1)
+            umma_ss(tmem + 256, umma_desc_sw128(sA + (k & 3) * 32, 16, 1024), umma_desc_sw128(sB + (k & 3) * 32, 16, 1024), idesc, 1u);
+          else
+            umma_ts(tmem + 256, tmem + 384 + k * 8, umma_desc_sw128(sB + k * 2048, 16384, 1024), idesc, 1u);
+        }
+        n += 8;
+        if ((n & 63) == 0) {   // bound the queue depth: wait for completion every 64 MMAs
+          __shared__ uint64_t bar;
+          if (n == 64) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+          umma_commit(smem_u32(&bar));
+          mbar_wait(smem_u32(&bar), ((n >> 6) - 1) & 1);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------
@@ -357,18 +462,51 @@ int main() {
   // ---- exp2 throughput --------------------------------------------------------------
   {
     float* dE;
-    CK(cudaMalloc(&dE, 148 * 256 * 4));
+    CK(cudaMalloc(&dE, 148 * 512 * 4));
     const char* en[3] = {"MUFU ex2.approx", "FMA-pipe polynomial exp2", "1:1 MUFU + polynomial"};
+    for (int nthr = 128; nthr <= 512; nthr *= 2)
     for (int mode = 0; mode < 3; ++mode) {
       const int iters = 2048;
-      probe_exp<<<prop.multiProcessorCount, 256>>>(dE, iters, mode, dCyc);
+      probe_exp<<<prop.multiProcessorCount, nthr>>>(dE, iters, mode, dCyc);
       CK(cudaDeviceSynchronize());
-      probe_exp<<<prop.multiProcessorCount, 256>>>(dE, iters, mode, dCyc);
+      probe_exp<<<prop.multiProcessorCount, nthr>>>(dE, iters, mode, dCyc);
       CK(cudaDeviceSynchronize());
       long long cyc;
       CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
-      double per_clk = (double)iters * 8 * 256 / (double)cyc;
-      printf("[RATE] %s : %.2f exp2 / clk / SM (8 warps, dependent chains x8)\n", en[mode], per_clk);
+      double per_clk = (double)iters * 8 * nthr / (double)cyc;
+      printf("[RATE] %s : %.2f exp2 / clk / SM (%d warps/SM, dependent chains x8)\n", en[mode], per_clk, nthr / 32);
+    }
+  }
+  // ---- TMEM read bandwidth ------------------------------------------------------------
+  {
+    float* dE;
+    CK(cudaMalloc(&dE, 148 * 512 * 4));
+    for (int with_exp = 0; with_exp < 2; ++with_exp)
+      for (int nthr = 128; nthr <= 512; nthr *= 2) {
+        const int iters = 512;
+        probe_ldtm<<<prop.multiProcessorCount, nthr>>>(dE, iters, with_exp, dCyc);
+        CK(cudaDeviceSynchronize());
+        probe_ldtm<<<prop.multiProcessorCount, nthr>>>(dE, iters, with_exp, dCyc);
+        CK(cudaDeviceSynchronize());
+        long long cyc;
+        CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
+        double bytes = (double)iters * 4 * 32 * 4 * nthr;
+        printf("[RATE] tcgen05.ld 32x32b.x32 %s: %.1f B / clk / SM (%d warps/SM; %.0f cycles per x32 per warp)\n",
+               with_exp ? "+32 ex2 each" : "(ld only)   ", bytes / cyc, nthr / 32, (double)cyc / (iters * 4));
+      }
+  }
+  {
+    float* dE;
+    CK(cudaMalloc(&dE, 512 * 4));
+    CK(cudaFuncSetAttribute(probe_ldtm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000));
+    const char* mm[3] = {"tensor pipe idle", "while SS M128N128 MMAs stream", "while TS M128N64 MMAs stream"};
+    for (int mode = 0; mode < 3; ++mode) {
+      const int iters = 256;
+      probe_ldtm_mma<<<1, 192, 70000>>>(dE, iters, mode, dCyc);
+      CK(cudaDeviceSynchronize());
+      long long cyc;
+      CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
+      printf("[RATE] tcgen05.ld x32 + wait, 4 warps, %s: %.0f cycles per load\n", mm[mode], (double)cyc / (iters * 4));
     }
   }
   printf("probe done, %d correctness failures\n", fails);

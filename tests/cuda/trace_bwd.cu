@@ -56,12 +56,13 @@ int main(int argc, char** argv) {
   }
   static long long tr[8][48][8];
   CK(cudaMemcpyFromSymbol(tr, g_fcsa_trace, sizeof(tr)));
-  long long t0 = tr[0][0][0];
-  const char* names[6] = {"MMA  [pre-Pwait, P_FULL seen, pre-DSwait, DS_FULL seen, DQ_EMPTY seen, iter issued]",
-                          "CMP0 [start, S_FULL seen, P arrived, DP_FULL seen, DS_FREE seen, DS arrived]",
-                          "CMP1 [same]", "RED  [DQ_FULL seen, ld done, stage free, reduce issued]",
-                          "TMA  [Q_EMPTY seen, DO_EMPTY seen]", "OBS  [S_FULL, DP_FULL, DQ_FULL complete]"};
-  int nslots[6] = {6, 6, 6, 4, 2, 3};
+  long long t0 = tr[1][0][0];
+  const char* names[6] = {"MMA  [S(i+1) issued, dV issued, dK issued, dP(i+1) issued, dQ issued]",
+                          "EXP  [top, S_FULL seen, S in regs, exps done, P arrived]",
+                          "DS   [top, P loaded, DP_FULL seen, DS_FREE ok, DS arrived]",
+                          "RED  [DQ_FULL seen, reduce issued]",
+                          "TMA  [Q_EMPTY seen, DO_EMPTY seen]", "OBS  [S_FULL, DP_FULL, PV_DONE, DQ_FULL complete]"};
+  int nslots[6] = {5, 5, 5, 2, 2, 4};
   for (int role = 0; role < 6; ++role) {
     printf("--- %s\n", names[role]);
     for (int i = 0; i < 12; ++i) {
@@ -72,7 +73,7 @@ int main(int argc, char** argv) {
   }
   // iteration period from the MMA role
   printf("MMA iteration period (cycles):");
-  for (int i = 1; i < 32; ++i) printf(" %lld", tr[0][i][1] - tr[0][i - 1][1]);
+  for (int i = 1; i < 32; ++i) printf(" %lld", tr[1][i][4] - tr[1][i - 1][4]);
   printf("\n");
   return 0;
 }
