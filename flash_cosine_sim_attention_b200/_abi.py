@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "fcsa_l2norm_forward",
     "fcsa_l2norm_backward",
     "fcsa_set_kernel_events",
+    "fcsa_forward_fused",
+    "fcsa_backward_fused",
 )
 
 
@@ -54,6 +56,11 @@ class FcsaProblem(Structure):
         ("key_mask", c_void_p),
         ("key_mask_stride", c_int64),
     ]
+
+
+class FcsaL2Norm(Structure):
+    _fields_ = [("groups", c_int32), ("q_hat", FcsaTensor), ("k_hat", FcsaTensor), ("q_rnorm", c_void_p),
+                ("k_rnorm", c_void_p)]
 
 
 class FcsaError(RuntimeError):
@@ -94,6 +101,11 @@ def load():
     lib.fcsa_l2norm_forward.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, c_void_p]
     lib.fcsa_l2norm_backward.restype = c_int32
     lib.fcsa_l2norm_backward.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, PT, c_void_p]
+    PN = POINTER(FcsaL2Norm)
+    lib.fcsa_forward_fused.restype = c_int32
+    lib.fcsa_forward_fused.argtypes = [PP, PT, PT, PT, PN, PT, c_void_p, c_void_p]
+    lib.fcsa_backward_fused.restype = c_int32
+    lib.fcsa_backward_fused.argtypes = [PP, PN, PT, PT, PT, c_void_p, PT, PT, PT, c_void_p, c_size_t, c_void_p]
     lib.fcsa_set_kernel_events.restype = c_int32
     lib.fcsa_set_kernel_events.argtypes = [c_int32, c_void_p, c_void_p]
     _lib = lib

@@ -33,6 +33,7 @@
 #include <type_traits>
 
 #include "../../include/fcsa_b200.h"
+#include "l2norm_kernels.cuh"
 #include "sm100_primitives.cuh"
 #include "tensor_map.h"
 
@@ -102,6 +103,7 @@ struct PrepArgs {
   const void* d_o; long long do_sb, do_sh, do_sn;
   const float* inv_l;               // (B, H, Nq)
   float* stats;
+  float* dq_acc;                    // zeroed here (32 bytes per thread) instead of a separate memset
 };
 
 template <typename T>
@@ -119,6 +121,11 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
   const int row = (int)(pr % padded);
   const int b = bh / a.H, h = bh % a.H;
   const bool valid = in && row < a.Nq;
+  if (in) {
+    uint4* z = reinterpret_cast<uint4*>(a.dq_acc) + (prow * tpr + tr) * 2;
+    z[0] = make_uint4(0, 0, 0, 0);
+    z[1] = make_uint4(0, 0, 0, 0);
+  }
   float dot = 0.f;
   if (valid) {
     const T* op = reinterpret_cast<const T*>(a.o) + b * a.o_sb + h * a.o_sh + (long long)row * a.o_sn + tr * 8;
@@ -157,6 +164,10 @@ struct BwdArgs {
   float* dk_acc; float* dv_acc;     // fp32 (B, Nk, D) accumulators when kv_heads == 1 < H
   void* dk; long long dk_sb, dk_sh, dk_sn;
   void* dv; long long dv_sb, dv_sh, dv_sn;
+  // when set, dk is the gradient w.r.t. the RAW keys: the l2norm backward
+  // (dk_hat - k_hat <k_hat, dk_hat>_group) * rnorm_group is applied in the epilogue
+  const float* k_rnorm;             // (B, H, Nk, G) or nullptr
+  int G;                            // groups (group size D/G >= 8 when k_rnorm is set)
 };
 
 template <typename T, int D>
@@ -592,6 +603,41 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tACC = lane_base + (w == 0 ? TM_DV : TM_DK);
     const float mul = (w == 0) ? 1.0f : a.scale;
     const bool shared_kv = (a.kv_heads == 1 && a.H > 1);
+    const bool fuse_l2 = (w == 1) && (a.k_rnorm != nullptr) && !shared_kv && NI > 0;
+    float gd[D / 8];                          // <k_hat, dk_hat> of the group each 8-feature segment is in
+    float rk[D / 8];
+    if (fuse_l2) {
+      float sd[D / 8];
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_x32(tACC + c * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int seg = 4 * c + s4;
+          const float4 kw = lds128f(sK + (seg >> 3) * 16384 + sw128_offset(r, seg & 7));
+          const float2 k0 = unpack2<T>(__float_as_uint(kw.x)), k1 = unpack2<T>(__float_as_uint(kw.y)),
+                       k2 = unpack2<T>(__float_as_uint(kw.z)), k3 = unpack2<T>(__float_as_uint(kw.w));
+          sd[seg] = __uint_as_float(acc[8 * s4 + 0]) * k0.x + __uint_as_float(acc[8 * s4 + 1]) * k0.y +
+                    __uint_as_float(acc[8 * s4 + 2]) * k1.x + __uint_as_float(acc[8 * s4 + 3]) * k1.y +
+                    __uint_as_float(acc[8 * s4 + 4]) * k2.x + __uint_as_float(acc[8 * s4 + 5]) * k2.y +
+                    __uint_as_float(acc[8 * s4 + 6]) * k3.x + __uint_as_float(acc[8 * s4 + 7]) * k3.y;
+        }
+      }
+      const int segs_per_group = (D / a.G) >> 3;            // power of two
+      int lg = 0;
+      while ((1 << lg) < segs_per_group) ++lg;
+      const long long rbase = (((long long)b * a.H + h) * a.Nk + (store_ok ? key_g : 0)) * a.G;
+#pragma unroll
+      for (int s0 = 0; s0 < D / 8; ++s0) {
+        float t = 0.f;
+#pragma unroll
+        for (int s1 = 0; s1 < D / 8; ++s1) t += ((s1 >> lg) == (s0 >> lg)) ? sd[s1] : 0.f;
+        gd[s0] = t;
+        rk[s0] = a.k_rnorm[rbase + (s0 >> lg)];
+      }
+    }
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t acc[32];
@@ -601,6 +647,24 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       } else {
 #pragma unroll
         for (int x = 0; x < 32; ++x) acc[x] = 0;
+      }
+      if (fuse_l2) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int seg = 4 * c + s4;
+          const float4 kw = lds128f(sK + (seg >> 3) * 16384 + sw128_offset(r, seg & 7));
+          const uint32_t kk[4] = {__float_as_uint(kw.x), __float_as_uint(kw.y), __float_as_uint(kw.z),
+                                  __float_as_uint(kw.w)};
+          const float m2 = rk[seg];              // mul (= scale) is applied below
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 kf = unpack2<T>(kk[e2]);
+            const float a0 = (__uint_as_float(acc[8 * s4 + 2 * e2]) - kf.x * gd[seg]) * m2;
+            const float a1 = (__uint_as_float(acc[8 * s4 + 2 * e2 + 1]) - kf.y * gd[seg]) * m2;
+            acc[8 * s4 + 2 * e2] = __float_as_uint(a0);
+            acc[8 * s4 + 2 * e2 + 1] = __float_as_uint(a1);
+          }
+        }
       }
       if (store_ok) {
         if (!shared_kv) {
@@ -639,7 +703,47 @@ struct DqFinishArgs {
   float scale;
   const float* dq_acc;
   void* dq; long long sb, sh, sn;
+  // when q_rnorm is set, dq is the gradient w.r.t. the RAW queries (l2norm backward applied here)
+  const void* q_hat; long long q_sb, q_sh, q_sn;
+  const float* q_rnorm;             // (B, H, Nq, G) or nullptr
+  int G;
 };
+
+// (dq_hat - q_hat <q_hat, dq_hat>_group) * rnorm_group on the 8 features one thread owns; the
+// `tpr` threads of a row are consecutive lanes, groups are aligned sub-blocks of them.
+template <typename T>
+__device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishArgs& a, bool ok, int b, int h,
+                                                  int row, int c8) {
+  if (a.q_rnorm == nullptr) return;            // uniform across the grid
+  float y[8];
+  {
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (ok)
+      raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh +
+                                            (long long)row * a.q_sn + c8 * 8);
+    const float2 u0 = unpack2<T>(raw.x), u1 = unpack2<T>(raw.y), u2 = unpack2<T>(raw.z), u3 = unpack2<T>(raw.w);
+    y[0] = u0.x; y[1] = u0.y; y[2] = u1.x; y[3] = u1.y; y[4] = u2.x; y[5] = u2.y; y[6] = u3.x; y[7] = u3.y;
+  }
+  const int gs = a.D / a.G;
+  const long long rbase = (((long long)b * a.H + h) * a.Nq + row) * a.G;
+  if (gs >= 8) {
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dot += y[i] * g[i];
+    const int tpg = gs >> 3;
+    for (int m = 1; m < tpg; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
+    const float rn = ok ? a.q_rnorm[rbase + c8 / tpg] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = (g[i] - y[i] * dot) * rn;
+  } else {
+    for (int g0 = 0; g0 < 8; g0 += gs) {
+      float dot = 0.f;
+      for (int i = 0; i < gs; ++i) dot += y[g0 + i] * g[g0 + i];
+      const float rn = ok ? a.q_rnorm[rbase + (c8 * 8 + g0) / gs] : 0.f;
+      for (int i = 0; i < gs; ++i) g[g0 + i] = (g[g0 + i] - y[g0 + i] * dot) * rn;
+    }
+  }
+}
 
 // D = 64: accumulator tile = [4 warps][16 feature-chunks][32 rows][4 features].
 // One thread = 8 consecutive features of one row.
@@ -647,23 +751,35 @@ template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs a) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long total = (long long)a.B * a.H * a.Nq * 8;
-  if (idx >= total) return;
-  const int c8 = (int)(idx & 7);
-  const long long rowid = idx >> 3;
+  const bool ok = idx < total;
+  const long long id = ok ? idx : 0;
+  const int c8 = (int)(id & 7);
+  const long long rowid = id >> 3;
   const int row = (int)(rowid % a.Nq);
   const int bh = (int)(rowid / a.Nq);
   const int b = bh / a.H, h = bh % a.H;
   const int qt = row >> 7, r = row & 127, wq = r >> 5, rl = r & 31;
   const float* tile = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048;
-  const float4 lo = *reinterpret_cast<const float4*>(tile + (2 * c8) * 128 + rl * 4);
-  const float4 hi = *reinterpret_cast<const float4*>(tile + (2 * c8 + 1) * 128 + rl * 4);
-  uint4 o4;
-  o4.x = pack2<T>(lo.x * a.scale, lo.y * a.scale);
-  o4.y = pack2<T>(lo.z * a.scale, lo.w * a.scale);
-  o4.z = pack2<T>(hi.x * a.scale, hi.y * a.scale);
-  o4.w = pack2<T>(hi.z * a.scale, hi.w * a.scale);
-  T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
-  *reinterpret_cast<uint4*>(dst) = o4;
+  float g[8];
+  {
+    float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+    if (ok) {
+      lo = *reinterpret_cast<const float4*>(tile + (2 * c8) * 128 + rl * 4);
+      hi = *reinterpret_cast<const float4*>(tile + (2 * c8 + 1) * 128 + rl * 4);
+    }
+    g[0] = lo.x * a.scale; g[1] = lo.y * a.scale; g[2] = lo.z * a.scale; g[3] = lo.w * a.scale;
+    g[4] = hi.x * a.scale; g[5] = hi.y * a.scale; g[6] = hi.z * a.scale; g[7] = hi.w * a.scale;
+  }
+  finish_l2norm_bwd<T>(g, a, ok, b, h, row, c8);
+  if (ok) {
+    uint4 o4;
+    o4.x = pack2<T>(g[0], g[1]);
+    o4.y = pack2<T>(g[2], g[3]);
+    o4.z = pack2<T>(g[4], g[5]);
+    o4.w = pack2<T>(g[6], g[7]);
+    T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
+    *reinterpret_cast<uint4*>(dst) = o4;
+  }
 }
 
 // D = 128: accumulator tile (64 query rows) = [4 warps][16 row-chunks][32 features][4 rows], i.e.
@@ -689,15 +805,21 @@ __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArg
   for (int e = threadIdx.x; e < 64 * 16; e += 256) {      // 16 x 8 features per row
     const int rr = e >> 4, c8 = e & 15;
     const int row = qt * 64 + rr;
-    if (row >= a.Nq) continue;
+    const bool ok = row < a.Nq;
     const float* s = &tile[rr][c8 * 8];
-    uint4 o4;
-    o4.x = pack2<T>(s[0] * a.scale, s[1] * a.scale);
-    o4.y = pack2<T>(s[2] * a.scale, s[3] * a.scale);
-    o4.z = pack2<T>(s[4] * a.scale, s[5] * a.scale);
-    o4.w = pack2<T>(s[6] * a.scale, s[7] * a.scale);
-    T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
-    *reinterpret_cast<uint4*>(dst) = o4;
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = s[i] * a.scale;
+    finish_l2norm_bwd<T>(g, a, ok, b, h, ok ? row : 0, c8);
+    if (ok) {
+      uint4 o4;
+      o4.x = pack2<T>(g[0], g[1]);
+      o4.y = pack2<T>(g[2], g[3]);
+      o4.z = pack2<T>(g[4], g[5]);
+      o4.w = pack2<T>(g[6], g[7]);
+      T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
+      *reinterpret_cast<uint4*>(dst) = o4;
+    }
   }
 }
 
@@ -740,6 +862,11 @@ struct BwdHostArgs {
   const float* inv_l;
   void* workspace;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // optional: recorded around the main kernel
+  // fused l2norm backward (q, k above are then the NORMALISED tensors and dq, dk the gradients
+  // w.r.t. the raw ones); both null = plain backward
+  const float* q_rnorm = nullptr;
+  const float* k_rnorm = nullptr;
+  int groups = 1;
 };
 
 template <typename T, int D>
@@ -755,9 +882,13 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
   const float log2e = 1.4426950408889634f;
   cudaError_t e;
 
-  // zero the fp32 accumulators (dq, and dk/dv when shared across heads)
-  e = cudaMemsetAsync(dq_acc, 0, w.total - w.dq_off, stream);
-  if (e != cudaSuccess) { *err = "cudaMemsetAsync(workspace)"; *ce = e; return FCSA_ERR_CUDA; }
+  // the dq accumulator is zeroed by the preprocess kernel; dk/dv accumulators (shared kv) here
+  if (shared_kv) {
+    e = cudaMemsetAsync(dkv_acc, 0, w.total - w.dkv_off, stream);
+    if (e != cudaSuccess) { *err = "cudaMemsetAsync(workspace)"; *ce = e; return FCSA_ERR_CUDA; }
+  }
+  const int gs = D / (h.groups > 0 ? h.groups : 1);
+  const bool fuse_k = h.k_rnorm != nullptr && !shared_kv && gs >= 8;
 
   // 1. preprocess
   {
@@ -766,7 +897,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     pa.c2 = h.shift * log2e;
     pa.o = h.o.ptr; pa.o_sb = h.o.sb; pa.o_sh = h.o.sh; pa.o_sn = h.o.sn;
     pa.d_o = h.d_o.ptr; pa.do_sb = h.d_o.sb; pa.do_sh = h.d_o.sh; pa.do_sn = h.d_o.sn;
-    pa.inv_l = h.inv_l; pa.stats = stats;
+    pa.inv_l = h.inv_l; pa.stats = stats; pa.dq_acc = dq_acc;
     const int rows_per_block = 256 / (D / 8);
     const long long rows = (long long)h.B * h.H * w.nqt * Cfg::QT;
     const long long grid = (rows + rows_per_block - 1) / rows_per_block;
@@ -794,6 +925,8 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     a.dk_acc = dkv_acc; a.dv_acc = dkv_acc + (size_t)h.B * h.Nk * D;
     a.dk = h.dk.ptr; a.dk_sb = h.dk.sb; a.dk_sh = h.dk.sh; a.dk_sn = h.dk.sn;
     a.dv = h.dv.ptr; a.dv_sb = h.dv.sb; a.dv_sh = h.dv.sh; a.dv_sn = h.dv.sn;
+    a.k_rnorm = fuse_k ? h.k_rnorm : nullptr;
+    a.G = h.groups;
     auto kern = fcsa_bwd_kernel<T, D>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -814,6 +947,8 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     DqFinishArgs fa;
     fa.B = h.B; fa.H = h.H; fa.Nq = h.Nq; fa.D = D; fa.nqt = w.nqt; fa.scale = h.scale;
     fa.dq_acc = dq_acc; fa.dq = h.dq.ptr; fa.sb = h.dq.sb; fa.sh = h.dq.sh; fa.sn = h.dq.sn;
+    fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
+    fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
     if (D == 64) {
       const long long total = (long long)h.B * h.H * h.Nq * 8;
       bwd_dq_finish64_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fa);
@@ -836,6 +971,21 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
         if (e != cudaSuccess) { *err = "dk/dv finish launch"; *ce = e; return FCSA_ERR_CUDA; }
         ++*launches;
       }
+    }
+    if (h.k_rnorm != nullptr && !fuse_k) {
+      // l2norm backward of dk as its own pass (shared keys/values, or groups finer than 8 features)
+      L2Args la;
+      la.B = h.B; la.H = h.kv_heads; la.N = h.Nk; la.D = D; la.G = h.groups;
+      la.x_sb = h.dk.sb; la.x_sh = h.dk.sh; la.x_sn = h.dk.sn;
+      la.y_sb = h.k.sb; la.y_sh = h.k.sh; la.y_sn = h.k.sn;
+      la.o_sb = h.dk.sb; la.o_sh = h.dk.sh; la.o_sn = h.dk.sn;
+      la.x = h.dk.ptr; la.y = h.k.ptr; la.dx = h.dk.ptr; la.rnorm = const_cast<float*>(h.k_rnorm);
+      const int rows_per_block = 256 / (D / 8);
+      const long long rows = (long long)la.B * la.H * la.N;
+      l2norm_bwd_kernel<T><<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), 256, 0, stream>>>(la);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) { *err = "l2norm backward (dk) launch"; *ce = e; return FCSA_ERR_CUDA; }
+      ++*launches;
     }
   }
   return FCSA_OK;

@@ -196,10 +196,11 @@ size_t fcsa_backward_workspace_bytes(const fcsa_problem* p) {
   return fcsa::bwd_workspace_bytes(p->batch, p->heads, p->kv_heads, p->seq_q, p->seq_k, p->head_dim);
 }
 
-int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
-                  const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
-                  const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
-                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream) {
+static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                         const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
+                         const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
+                         const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream,
+                         const float* q_rnorm, const float* k_rnorm, int groups) {
   int r;
   if ((r = check_problem(p))) return r;
   if ((r = check_tensor(q, "q")) || (r = check_tensor(k, "k")) || (r = check_tensor(v, "v")) ||
@@ -223,6 +224,9 @@ int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor
   h.workspace = workspace;
   h.ev_start = g_ev[1][0];
   h.ev_stop = g_ev[1][1];
+  h.q_rnorm = q_rnorm;
+  h.k_rnorm = k_rnorm;
+  h.groups = groups;
   int launches = 0;
   const char* err = nullptr;
   cudaError_t ce = cudaSuccess;
@@ -231,6 +235,66 @@ int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor
   if (r == FCSA_ERR_CUDA) return fail(r, "%s: %s", err ? err : "backward", cudaGetErrorString(ce));
   if (r != FCSA_OK) return fail(r, "%s", err ? err : "backward failed");
   return FCSA_OK;
+}
+
+int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                  const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
+                  const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
+                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, stream,
+                       nullptr, nullptr, 1);
+}
+
+int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                       const fcsa_tensor* v, const fcsa_l2norm* n, const fcsa_tensor* o, float* inv_l,
+                       void* stream) {
+  int r;
+  if ((r = check_problem(p))) return r;
+  if (!n) return fail(FCSA_ERR_INVALID, "null fcsa_l2norm");
+  if ((r = check_l2(p->dtype, p->batch, p->heads, p->seq_q, p->head_dim, n->groups))) return r;
+  if ((r = check_tensor(q, "q")) || (r = check_tensor(k, "k")) || (r = check_tensor(&n->q_hat, "q_hat")) ||
+      (r = check_tensor(&n->k_hat, "k_hat")))
+    return r;
+  if (!n->q_rnorm || !n->k_rnorm) return fail(FCSA_ERR_INVALID, "q_rnorm / k_rnorm: null");
+  fcsa::L2PairArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  const fcsa_tensor* src[2] = {q, k};
+  const fcsa_tensor* dst[2] = {&n->q_hat, &n->k_hat};
+  float* rn[2] = {n->q_rnorm, n->k_rnorm};
+  const int heads[2] = {p->heads, p->kv_heads};
+  const int rows[2] = {p->seq_q, p->seq_k};
+  long long max_rows = 0;
+  for (int t = 0; t < 2; ++t) {
+    fcsa::L2Args& a = pa.t[t];
+    a.B = p->batch; a.H = heads[t]; a.N = rows[t]; a.D = p->head_dim; a.G = n->groups;
+    a.x_sb = src[t]->sb; a.x_sh = src[t]->sh; a.x_sn = src[t]->sn;
+    a.y_sb = dst[t]->sb; a.y_sh = dst[t]->sh; a.y_sn = dst[t]->sn;
+    a.x = src[t]->ptr; a.y = dst[t]->ptr; a.rnorm = rn[t];
+    const long long nr = (long long)a.B * a.H * a.N;
+    if (nr > max_rows) max_rows = nr;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int rows_per_block = 2 * (256 / (p->head_dim / 8));
+  dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), 2);
+  if (p->dtype == FCSA_BF16) fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(pa);
+  else fcsa::l2norm_fwd_pair_kernel<__half><<<grid, 256, 0, s>>>(pa);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "l2norm (q, k) launch");
+  g_launches.fetch_add(1);
+  return fcsa_forward(p, &n->q_hat, &n->k_hat, v, o, inv_l, stream);
+}
+
+int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_tensor* v,
+                        const fcsa_tensor* o, const fcsa_tensor* d_o, const float* inv_l,
+                        const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!n) return fail(FCSA_ERR_INVALID, "null fcsa_l2norm");
+  int r;
+  if ((r = check_problem(p))) return r;
+  if ((r = check_l2(p->dtype, p->batch, p->heads, p->seq_q, p->head_dim, n->groups))) return r;
+  if (!n->q_rnorm || !n->k_rnorm) return fail(FCSA_ERR_INVALID, "q_rnorm / k_rnorm: null");
+  return backward_impl(p, &n->q_hat, &n->k_hat, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes,
+                       stream, n->q_rnorm, n->k_rnorm, n->groups);
 }
 
 int fcsa_l2norm_forward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,

@@ -329,7 +329,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     // ---- epilogue: O * 1/max(l, eps) -> global ----------------------------------------
-    const float inv = 1.0f / fmaxf(l, 1e-10f);
+    // the clamp only guards rows with no visible key (l == 0, O == 0 -> o = 0; reference: cu:1239 uses
+    // 1e-10, too large here because shift = scale*groups makes legitimately tiny row sums)
+    const float inv = 1.0f / fmaxf(l, 1e-37f);
     const bool row_ok = row_g < a.Nq;
     T* orow = reinterpret_cast<T*>(a.o) + (long long)b * a.o_sb + (long long)h * a.o_sh +
               (long long)row_g * a.o_sn;

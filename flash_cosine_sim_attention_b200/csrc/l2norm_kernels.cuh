@@ -82,6 +82,80 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
   }
 }
 
+// q and k in one launch (blockIdx.y selects the tensor), two rows per thread so that two
+// independent 16-byte loads are in flight before the first reduction.
+struct L2PairArgs {
+  L2Args t[2];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
+  const L2Args& a = pa.t[blockIdx.y];
+  const int tpr = a.D >> 3;
+  const int rows_per_block = 256 / tpr;
+  const long long total_rows = (long long)a.B * a.H * a.N;
+  const int tr = threadIdx.x % tpr;
+  const int gs = a.D / a.G;
+  long long row[2];
+  bool ok[2];
+  uint4 raw[2];
+  const T* xp[2];
+  int bb[2], hh[2], nn[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    row[u] = ((long long)blockIdx.x * 2 + u) * rows_per_block + threadIdx.x / tpr;
+    ok[u] = row[u] < total_rows;
+    const long long rr = ok[u] ? row[u] : 0;
+    nn[u] = (int)(rr % a.N);
+    hh[u] = (int)((rr / a.N) % a.H);
+    bb[u] = (int)(rr / ((long long)a.N * a.H));
+    xp[u] = reinterpret_cast<const T*>(a.x) + bb[u] * a.x_sb + hh[u] * a.x_sh + nn[u] * a.x_sn + tr * 8;
+    raw[u] = make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(xp[u]);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    float f[8];
+    {
+      float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
+      f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y; f[4] = t2.x; f[5] = t2.y; f[6] = t3.x; f[7] = t3.y;
+    }
+    float rn[8];
+    if (gs >= 8) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+      const int tpg = gs >> 3;
+      ss = group_reduce(ss, tpg);
+      const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rn[i] = r;
+      if (ok[u] && a.rnorm && (tr % tpg) == 0) a.rnorm[row[u] * a.G + tr / tpg] = r;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rn[i] = 0.f;
+      for (int g0 = 0; g0 < 8; g0 += gs) {
+        float ss = 0.f;
+        for (int i = 0; i < gs; ++i) ss += f[g0 + i] * f[g0 + i];
+        const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        for (int i = 0; i < gs; ++i) rn[g0 + i] = r;
+        if (ok[u] && a.rnorm) a.rnorm[row[u] * a.G + (tr * 8 + g0) / gs] = r;
+      }
+    }
+    if (ok[u]) {
+      uint4 w;
+      w.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
+      w.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
+      w.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
+      w.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
+      T* yp = reinterpret_cast<T*>(a.y) + bb[u] * a.y_sb + hh[u] * a.y_sh + nn[u] * a.y_sn + tr * 8;
+      *reinterpret_cast<uint4*>(yp) = w;
+    }
+  }
+}
+
 // dx = (dy - y * <y, dy>_group) * rnorm_group
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const L2Args a) {

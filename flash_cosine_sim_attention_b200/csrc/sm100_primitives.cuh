@@ -354,7 +354,9 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
 template <>
 __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  // satfinite: an out-of-range value becomes +-65504 instead of inf (fp16 has no headroom for
+  // exp(scale * q.k) when grouped l2norm lets q.k exceed 1)
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 

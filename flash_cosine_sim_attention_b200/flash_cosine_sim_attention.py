@@ -170,6 +170,57 @@ def _attn_backward(do, o, inv_l, q, k, v, mask_u8, scale, shift, causal):
     return dq, dk, dv
 
 
+def _l2norm_struct(sh, groups, qn, kn, rq, rk):
+    n = _abi.FcsaL2Norm()
+    n.groups = groups
+    n.q_hat, n.k_hat = _view4(qn, sh.qkind), _view4(kn, sh.kkind)
+    n.q_rnorm, n.k_rnorm = rq.data_ptr(), rk.data_ptr()
+    return n
+
+
+def _attn_forward_fused(q, k, v, mask_u8, scale, shift, causal, groups, need_inv_l=True):
+    """raw q, k -> (o, inv_l, q_hat, k_hat, q_rnorm, k_rnorm) through fcsa_forward_fused: one
+    launch normalises q and k, one runs the attention."""
+    lib = _abi.load()
+    sh = _Shapes(q, k, v)
+    q, k, v = _tma_ready(q), _tma_ready(k), _tma_ready(v)
+    dev = q.device
+    o = torch.empty(q.shape, dtype=q.dtype, device=dev)
+    qn = torch.empty(q.shape, dtype=q.dtype, device=dev)
+    kn = torch.empty(k.shape, dtype=k.dtype, device=dev)
+    rq = torch.empty((sh.B, sh.H, sh.Nq, groups), dtype=torch.float32, device=dev)
+    rk = torch.empty((sh.B, sh.kv_heads, sh.Nk, groups), dtype=torch.float32, device=dev)
+    inv_l = torch.empty((sh.B, sh.H, sh.Nq), dtype=torch.float32, device=dev) if need_inv_l else None
+    p = _problem(sh, q.dtype, scale, shift, causal, mask_u8)
+    n = _l2norm_struct(sh, groups, qn, kn, rq, rk)
+    with torch.cuda.device(dev):
+        _abi.check(lib.fcsa_forward_fused(_abi.ref(p), _abi.ref(_view4(q, sh.qkind)), _abi.ref(_view4(k, sh.kkind)),
+                                          _abi.ref(_view4(v, sh.kkind)), _abi.ref(n), _abi.ref(_view4(o, sh.qkind)),
+                                          inv_l.data_ptr() if need_inv_l else None, _stream(dev)))
+    return o, inv_l, qn, kn, rq, rk
+
+
+def _attn_backward_fused(do, o, inv_l, qn, kn, v, rq, rk, mask_u8, scale, shift, causal, groups):
+    """gradients w.r.t. the raw q, k and v through fcsa_backward_fused."""
+    lib = _abi.load()
+    sh = _Shapes(qn, kn, v)
+    v, o, do = _tma_ready(v), _tma_ready(o), _tma_ready(do)
+    dev = qn.device
+    dq = torch.empty(qn.shape, dtype=qn.dtype, device=dev)
+    dk = torch.empty(kn.shape, dtype=kn.dtype, device=dev)
+    dv = torch.empty(v.shape, dtype=v.dtype, device=dev)
+    p = _problem(sh, qn.dtype, scale, shift, causal, mask_u8)
+    n = _l2norm_struct(sh, groups, qn, kn, rq, rk)
+    nbytes = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(lib.fcsa_backward_fused(
+            _abi.ref(p), _abi.ref(n), _abi.ref(_view4(v, sh.kkind)), _abi.ref(_view4(o, sh.qkind)),
+            _abi.ref(_view4(do, sh.qkind)), inv_l.data_ptr(), _abi.ref(_view4(dq, sh.qkind)),
+            _abi.ref(_view4(dk, sh.kkind)), _abi.ref(_view4(dv, sh.kkind)), ws.data_ptr(), nbytes, _stream(dev)))
+    return dq, dk, dv
+
+
 def _l2norm_forward(x, groups):
     """CUDA kernel: x -> (x normalised per group, 1/norm) with x 3-D or 4-D."""
     lib = _abi.load()
@@ -256,6 +307,24 @@ class FlashCosineSimAttention(Function):
 flash_cosine_sim_attention_cuda = FlashCosineSimAttention.apply
 
 
+def _choose_shift(dtype, scale, groups, l2norm_qk):
+    """Constant subtracted from the logits before exp (any constant gives the same attention;
+    the reference hard-codes `scale`, cu:1216).  p = exp(logit - shift) is stored in 16 bit:
+      bf16: shift = scale*groups - p <= 1 for every possible q.k (<= groups); bf16 has fp32's range.
+      fp16, groups == 1: q.k <= 1, so shift = scale - 15 ln 2 puts p in (0, 2^15]: the top of the
+            fp16 range instead of its subnormals.
+      fp16, groups > 1: exp(scale*q.k) spans e^(2*scale*groups) - more than fp16 can hold without a
+            row max.  Same choice as the reference (shift = scale); the kernels saturate p at
+            65504 instead of producing inf.  Use bf16 for grouped l2norm with large scale*groups."""
+    if not l2norm_qk:
+        return float(scale)
+    if dtype == torch.bfloat16:
+        return float(scale * groups)
+    if groups == 1:
+        return float(scale) - 15.0 * math.log(2.0)
+    return float(scale)
+
+
 class _FusedCosineSimAttention(Function):
     """One autograd node for l2norm(q), l2norm(k) -> attention, all in CUDA kernels."""
 
@@ -263,14 +332,14 @@ class _FusedCosineSimAttention(Function):
     def forward(ctx, q, k, v, mask, scale, causal, groups, l2norm_qk):
         sh = _Shapes(q, k, v)
         mask_u8 = _prep_mask(mask, sh)
-        shift = scale * groups if l2norm_qk else scale
+        shift = _choose_shift(q.dtype, scale, groups, l2norm_qk)
+        needs_grad = any(ctx.needs_input_grad[:3])
         if l2norm_qk:
-            qn, rq = _l2norm_forward(q, groups)
-            kn, rk = _l2norm_forward(k, groups)
+            o, inv_l, qn, kn, rq, rk = _attn_forward_fused(q, k, v, mask_u8, scale, shift, causal, groups,
+                                                           need_inv_l=needs_grad)
         else:
             qn, kn, rq, rk = q, k, None, None
-        needs_grad = any(ctx.needs_input_grad[:3])
-        o, inv_l = _attn_forward(qn, kn, v, mask_u8, scale, shift, causal, need_inv_l=needs_grad)
+            o, inv_l = _attn_forward(qn, kn, v, mask_u8, scale, shift, causal, need_inv_l=needs_grad)
         if needs_grad:
             ctx.save_for_backward(o, inv_l, qn, kn, v, mask_u8, rq, rk)
             ctx.params = (scale, shift, causal, groups, l2norm_qk)
@@ -280,10 +349,10 @@ class _FusedCosineSimAttention(Function):
     def backward(ctx, do):
         o, inv_l, qn, kn, v, mask_u8, rq, rk = ctx.saved_tensors
         scale, shift, causal, groups, l2norm_qk = ctx.params
-        dq, dk, dv = _attn_backward(do, o, inv_l, qn, kn, v, mask_u8, scale, shift, causal)
         if l2norm_qk:
-            dq = _l2norm_backward(dq, qn, rq, groups)
-            dk = _l2norm_backward(dk, kn, rk, groups)
+            dq, dk, dv = _attn_backward_fused(do, o, inv_l, qn, kn, v, rq, rk, mask_u8, scale, shift, causal, groups)
+        else:
+            dq, dk, dv = _attn_backward(do, o, inv_l, qn, kn, v, mask_u8, scale, shift, causal)
         return dq, dk, dv, None, None, None, None, None
 
 

@@ -84,7 +84,7 @@ const char* fcsa_last_error(void);
 int64_t fcsa_debug(void);
 
 /*
- * o = softmax-like(q k^T) v with the fixed-shift formulation; inv_l[b][h][i] = 1 / max(l_i, 1e-10)
+ * o = softmax-like(q k^T) v with the fixed-shift formulation; inv_l[b][h][i] = 1 / max(l_i, 1e-37)
  * is the saved normaliser the backward needs (the reference's `l` output, cu:1698/1239).
  * inv_l: (batch, heads, seq_q) fp32 contiguous, may be NULL when no backward will follow.
  * mask and causal are mutually exclusive (flash_cosine_sim_attention.py:88, cu:1675).
@@ -124,6 +124,35 @@ int fcsa_l2norm_backward(int32_t dtype, int32_t batch, int32_t heads, int32_t ro
                          int32_t head_dim, int32_t groups, const fcsa_tensor* dy,
                          const fcsa_tensor* y, const float* rnorm, const fcsa_tensor* dx,
                          void* stream);
+
+/*
+ * Fused variants: the grouped l2-normalisation of q and k that the reference performs with PyTorch
+ * ops around its kernels (flash_cosine_sim_attention.py:320-321, l2norm_tensors py:57-65) and its
+ * autograd backward run inside the same call.
+ *   q_hat, k_hat : normalised q / k in the problem dtype - outputs of fcsa_forward_fused, inputs of
+ *                  fcsa_backward_fused (the reference saves exactly these for its backward, py:270)
+ *   q_rnorm      : (batch, heads, seq_q, groups)    fp32 = 1 / max(||q||_group, 1e-12)
+ *   k_rnorm      : (batch, kv_heads, seq_k, groups) fp32
+ * head_dim / groups must be a power of two.
+ */
+typedef struct fcsa_l2norm {
+  int32_t groups;
+  fcsa_tensor q_hat, k_hat;
+  float* q_rnorm;
+  float* k_rnorm;
+} fcsa_l2norm;
+
+/* q_hat, k_hat = l2norm(q), l2norm(k); o, inv_l = fcsa_forward(q_hat, k_hat, v). */
+int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                       const fcsa_tensor* v, const fcsa_l2norm* n, const fcsa_tensor* o, float* inv_l,
+                       void* stream);
+
+/* Gradients w.r.t. the RAW q, k (and v): fcsa_backward followed by the l2norm backward, the latter
+ * folded into the dq finish pass and the dk epilogue.  Same workspace as fcsa_backward. */
+int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_tensor* v,
+                        const fcsa_tensor* o, const fcsa_tensor* d_o, const float* inv_l,
+                        const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Measurement hook (bench.py roofline line; no reference counterpart - the reference only timed

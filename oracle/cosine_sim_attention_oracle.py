@@ -44,6 +44,21 @@ def l2norm_backward(dy, x, groups=1, eps=1e-12):
     return ((d - y * (y * d).sum(-1, keepdims=True)) / n).reshape(shape)
 
 
+def round_to(x, fmt):
+    """Round float64 values to the nearest bf16 / fp16 value (ties to even), back as float64.
+    The reference casts the normalised q, k back to the input dtype before they enter the
+    attention (py:64); 16-bit parity runs have to model that rounding."""
+    if fmt is None:
+        return x
+    if fmt in ("f16", "float16"):
+        return np.asarray(x, dtype=np.float32).astype(np.float16).astype(F64)
+    if fmt in ("bf16", "bfloat16"):
+        u = np.ascontiguousarray(np.asarray(x, dtype=np.float32)).view(np.uint32).astype(np.uint64)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+        return u.astype(np.uint32).view(np.float32).reshape(np.shape(x)).astype(F64)
+    raise ValueError(fmt)
+
+
 def _canon(q, k, v):
     """reference py:90-97: 3-D q = merged batch-heads (then k, v must be 3-D too);
     3-D k with 4-D q = one key/value head shared by all query heads."""
@@ -72,7 +87,7 @@ def _visibility(b_idx, Nq, Nk, mask, causal):
 
 
 def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=False, l2norm_qk=True,
-              attn_bias_batch_dim=False, d_out=None, empty_rows="mean"):
+              attn_bias_batch_dim=False, d_out=None, empty_rows="mean", round_qk=None):
     """Forward (and, when d_out is given, backward) of cosine-sim attention in float64.
 
     Forward: reference py:75-126 - normalise q, k (py:99-100); sim = scale * q k^T (py:102-104);
@@ -85,6 +100,10 @@ def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=Fals
     empty_rows: what a query with no visible key yields - "mean" (plain reference: softmax of an
     all-(-max) row = uniform average of v) or "zero" (the fused kernels, cu:1239: 1/max(l, eps)).
 
+    round_qk: None | "bf16" | "f16" - round the NORMALISED q, k to that format before the
+    similarity (what the reference's l2norm_tensors does for 16-bit inputs, py:64); gradients flow
+    through the rounding unchanged, as autograd does through a dtype cast.
+
     Returns o, or (o, dq, dk, dv) when d_out is given.  Shapes follow the inputs."""
     assert not (causal and mask is not None), "mask should not be supplied if causality is needed"
     q0, k0, v0 = (np.asarray(t, dtype=F64) for t in (q, k, v))
@@ -96,6 +115,7 @@ def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=Fals
     if l2norm_qk:
         qn, _ = l2norm(q4, groups)
         kn, _ = l2norm(k4, groups)
+        qn, kn = round_to(qn, round_qk), round_to(kn, round_qk)
     else:
         qn, kn = q4, k4
     o = np.zeros((B, H, Nq, D), dtype=F64)

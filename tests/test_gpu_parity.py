@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 TOL_OUT = {torch.bfloat16: 1e-2, torch.float16: 2e-3}
 TOL_GRAD = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
 BWD_HEAD_DIMS = (64, 128)
+ROUND = {torch.bfloat16: "bf16", torch.float16: "f16"}   # the op stores normalised q, k in the input dtype
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +68,8 @@ def check(fcsa, qs, kvs, dtype, seed=0, mask_p=None, grads=True, amp=1.0, **kw):
     assert o.shape == q.shape and o.dtype == dtype
     ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(),
                            mask=None if mask is None else mask.numpy(),
-                           d_out=do.float().numpy() if grads else None, empty_rows="zero", **kw)
+                           d_out=do.float().numpy() if grads else None, empty_rows="zero",
+                           round_qk=ROUND[dtype], **kw)
     if not grads:
         assert rel_err(o, ref) <= TOL_OUT[dtype]
         return
@@ -128,6 +130,12 @@ def test_causal_cross_lengths(fcsa, qn, kn):
 
 @pytest.mark.parametrize("groups,scale", [(2, 8), (4, 10), (8, 1), (16, 4)])
 def test_groups_and_scales(fcsa, groups, scale):
+    check(fcsa, (1, 4, 300, 64), (1, 4, 300, 64), torch.bfloat16, seed=groups, groups=groups, scale=scale)
+
+
+@pytest.mark.parametrize("groups,scale", [(1, 10), (2, 8), (8, 1)])
+def test_groups_and_scales_fp16(fcsa, groups, scale):
+    """fp16 holds exp(scale*q.k) only while scale*groups stays moderate (see _choose_shift)."""
     check(fcsa, (1, 4, 300, 64), (1, 4, 300, 64), torch.float16, seed=groups, groups=groups, scale=scale)
 
 

@@ -94,3 +94,10 @@ def test_gradients_match_finite_differences():
         args_m = [m if a is arr else a for a in (q, k, v)]
         fd = (f(*args_p) - f(*args_m)) / (2 * eps)
         assert abs(fd - grad[idx]) < 1e-6
+
+
+def test_round_to_matches_torch():
+    import torch
+    x = np.random.default_rng(19).standard_normal(4096) * np.exp(np.random.default_rng(20).uniform(-20, 20, 4096))
+    assert np.array_equal(oracle.round_to(x, "bf16"), torch.from_numpy(x).float().bfloat16().double().numpy())
+    assert np.array_equal(oracle.round_to(x, "f16"), torch.from_numpy(x).float().half().double().numpy())
