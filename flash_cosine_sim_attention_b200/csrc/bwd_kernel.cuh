@@ -63,7 +63,7 @@ struct BwdCfg {
 
 // ------------------------------------------------------------------------------------------
 // workspace layout (all fp32):
-//   stats : [B*H][nqt][2][QT]      c3 then delta for each query tile (padded rows = 0)
+//   stats : [B*H][nqt][2][QT]      c3 then -delta for each query tile (padded rows = 0)
 //   dq_acc: [B*H][nqt][4 warps][16 chunks][32 lanes][4]   32 KB per query tile, in the order the
 //           reduce warps produce it (D = 64: lane = query row, chunk = 4 features;
 //           D = 128: lane = feature, chunk = 4 query rows)
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
       dl = dot;
     }
     st[r] = c3;
-    st[a.QT + r] = dl;
+    st[a.QT + r] = -dl;      // stored negated: the dS stage computes P * (dP + (-delta)) with packed adds
   }
 }
 
@@ -505,8 +505,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(s[c & 1][e]), c1, c3v[e]));
-              float p1 = ex2_approx(fmaf(__uint_as_float(s[c & 1][e + 1]), c1, c3v[e + 1]));
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c & 1][e]), __uint_as_float(s[c & 1][e + 1])),
+                                          make_float2(c1, c1), make_float2(c3v[e], c3v[e + 1]));
+              float p0 = ex2_approx(x.x);
+              float p1 = ex2_approx(x.y);
               if (MASKED) {
                 const int cc = 32 * c + e;
                 p0 = (cc >= lo && cc <= hi) ? p0 : 0.f;
@@ -568,9 +570,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const float2 pa = unpack2<T>(pp[c & 1][e / 2]);
-            const float d0 = pa.x * (__uint_as_float(d[c & 1][e]) - dlv[e]);
-            const float d1 = pa.y * (__uint_as_float(d[c & 1][e + 1]) - dlv[e + 1]);
-            pk[e / 2] = pack2<T>(d0, d1);
+            const float2 t = __fadd2_rn(make_float2(__uint_as_float(d[c & 1][e]), __uint_as_float(d[c & 1][e + 1])),
+                                        make_float2(dlv[e], dlv[e + 1]));        // dP - delta (delta stored negated)
+            const float2 ds = __fmul2_rn(pa, t);
+            pk[e / 2] = pack2<T>(ds.x, ds.y);
           }
           if (c == 0) {
             mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);        // the dQ product of tile i-1 has left smem dS

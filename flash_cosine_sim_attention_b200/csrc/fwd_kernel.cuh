@@ -7,7 +7,8 @@
 //
 //   * one CTA owns 256 query rows of one (batch, head): two 128-row tiles that ping-pong
 //   * warp 8   : TMA producer   (Q once, K and V tiles through mbarrier rings)
-//   * warp 9   : tcgen05 issuer (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with P_t read from TMEM)
+//   * warps 9,10: tcgen05 issuers, one per query tile (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with
+//                P_t read from TMEM); warp 11 idles
 //   * warps 0-3: "softmax" warpgroup for tile 0, warps 4-7 for tile 1: thread == query row,
 //                tcgen05.ld S -> exp2(fma) -> row sum in a register -> 16-bit P -> tcgen05.st
 //   * TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).  Because there is
@@ -20,6 +21,10 @@
 #pragma once
 
 #include "sm100_primitives.cuh"
+
+#ifndef FCSA_POLY_EVERY
+#define FCSA_POLY_EVERY 4   // forward, D = 64: 1 of every N exp pairs runs on the FMA pipe (0 = none)
+#endif
 
 namespace fcsa {
 
@@ -48,11 +53,11 @@ struct FwdCfg {
   static constexpr int kOffV = kOffK + kKS * kTile;
   static constexpr int kOffBar = kOffV + kVS * kTile;
   static constexpr int kSmem = kOffBar + 256 + 1024;  // + alignment slack
-  static constexpr int kThreads = 320;
+  static constexpr int kThreads = 384;
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FwdArgs a) {
   using Cfg = FwdCfg<D>;
@@ -73,6 +78,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 V_EMPTY = V_FULL + VS, S_FULL = V_EMPTY + VS, P_FULL = S_FULL + 2,
                 O_FULL = P_FULL + 2, S_FREE = O_FULL + 2, P_FREE = S_FREE + 2, NBARS = P_FREE + 2;
   constexpr bool PSEP = (D == 64);     // P in its own TMEM columns (see header comment)
+  constexpr int kPolyEvery = (D == 64) ? FCSA_POLY_EVERY : 8;   // 1 of every N exp pairs is emulated on the FMA pipe
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,11 +117,11 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(BAR(Q_FULL), 1);
     for (int i = 0; i < KS; ++i) {
       mbar_init(BAR(K_FULL + i), 1);
-      mbar_init(BAR(K_EMPTY + i), 1);
+      mbar_init(BAR(K_EMPTY + i), 2);
     }
     for (int i = 0; i < VS; ++i) {
       mbar_init(BAR(V_FULL + i), 1);
-      mbar_init(BAR(V_EMPTY + i), 1);
+      mbar_init(BAR(V_EMPTY + i), 2);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(BAR(S_FULL + t), 1);
@@ -160,15 +166,18 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_load_4d(sV + vs * TILE + ch * 16384, &tm_v, BAR(V_FULL + vs), ch * 64, j * 128, hk, b);
       }
     }
-  } else if (warp == 9) {
-    // =============================== MMA issuer =================================
+  } else if (warp == 9 || warp == 10) {
+    // =============================== MMA issuers ================================
+    // One issuing thread per query tile (warp 9: tile 0, warp 10: tile 1).  Each follows only its
+    // own softmax warpgroup (S_t(j+1) when S_t(j) is in registers, P_t(j) V_j when P_t(j) is stored),
+    // so neither tile ever waits behind the other's barriers; the tensor pipe interleaves the two
+    // instruction streams.  K / V ring slots are released by both (barrier count 2).
+    const int t = warp - 9;
     if (NT > 0 && elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc<T>(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc<T>(128, D, 0, 1);
-      mbar_wait(BAR(Q_FULL), 0);
-      tc_fence_after();
-
-      auto issue_S = [&](int t, int j) {
+      const int nt = n_t[t];
+      auto issue_S = [&](int j) {
         const int ks = j % KS;
         mbar_wait(BAR(K_FULL + ks), (j / KS) & 1);
         tc_fence_after();
@@ -179,56 +188,54 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                   umma_desc_sw128(sK + ks * TILE + o, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(BAR(S_FULL + t));
+        umma_commit(BAR(K_EMPTY + ks));          // this tile's share of the release of K_j
       };
-
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (n_t[t] > 0) issue_S(t, 0);
-      umma_commit(BAR(K_EMPTY + 0));
-
+      if (nt > 0) {
+        mbar_wait(BAR(Q_FULL), 0);
+        tc_fence_after();
+        // The two softmax warpgroups share the MUFU pipe: started half a tile apart, one computes at
+        // full rate while the other is in its per-tile overhead (TMEM load/store, barriers).
+        if (t == 1 && n_t[0] > 0) mbar_wait(BAR(P_FULL + 0), 0);
+        issue_S(0);
+      }
       for (int j = 0; j < NT; ++j) {
         const int vs = j % VS;
-        if (PSEP) {
-          // next S tiles first: they only need the softmax warpgroup to have pulled S(j) into registers
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (j + 1 < n_t[t]) {
-              mbar_wait(BAR(S_FREE + t), j & 1);
-              FCSA_TR(0, j, t);
-              tc_fence_after();
-              issue_S(t, j + 1);
-            }
-          }
-          if (j + 1 < NT) umma_commit(BAR(K_EMPTY + (j + 1) % KS));
-        }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j < n_t[t]) {
-            mbar_wait(BAR(P_FULL + t), j & 1);
-            FCSA_TR(0, j, 2 + 2 * t);
-            mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
-            FCSA_TR(0, j, 3 + 2 * t);
+        if (j < nt) {
+          if (PSEP && j + 1 < nt) {
+            mbar_wait(BAR(S_FREE + t), j & 1);   // S_t(j) sits in registers: produce S_t(j+1) now
+            FCSA_TR(0, j, t);
             tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              umma_ts(tmem + 256 + t * D, tmem + (PSEP ? 384 + t * 64 : t * 128 + 64) + k * 8,
-                      umma_desc_sw128(sV + vs * TILE + k * 2048, 16384, 1024), idesc_o,
-                      (j > 0 || k > 0) ? 1u : 0u);
-            }
-            if (PSEP) {
-              umma_commit(BAR(P_FREE + t));
-              if (j + 1 >= n_t[t]) umma_commit(BAR(O_FULL + t));
-            } else {
-              if (j + 1 < n_t[t]) issue_S(t, j + 1);
-              else umma_commit(BAR(O_FULL + t));
-            }
+            issue_S(j + 1);
           }
+          mbar_wait(BAR(P_FULL + t), j & 1);
+          FCSA_TR(0, j, 2 + 2 * t);
+          mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_ts(tmem + 256 + t * D, tmem + (PSEP ? 384 + t * 64 : t * 128 + 64) + k * 8,
+                    umma_desc_sw128(sV + vs * TILE + k * 2048, 16384, 1024), idesc_o,
+                    (j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(BAR(V_EMPTY + vs));
+          if (PSEP) umma_commit(BAR(P_FREE + t));
+          if (j + 1 < nt) {
+            if (!PSEP) issue_S(j + 1);           // P_t aliases S_t: S_t(j+1) goes behind P_t(j) V_j
+          } else {
+            umma_commit(BAR(O_FULL + t));
+          }
+        } else {
+          // this tile has no work on key tile j (causal: tile 0 ends one key tile before tile 1;
+          // or the tile is past the end of q): still release the ring slots the other tile uses
+          // (paced by the fills: one arrival per refill of the slot, never two in one phase)
+          mbar_wait(BAR(K_FULL + j % KS), (j / KS) & 1);
+          mbar_arrive(BAR(K_EMPTY + j % KS));
+          mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
+          mbar_arrive(BAR(V_EMPTY + vs));
         }
-        umma_commit(BAR(V_EMPTY + vs));
-        if (!PSEP && j + 1 < NT) umma_commit(BAR(K_EMPTY + (j + 1) % KS));
       }
     }
-  } else {
+  } else if (warp < 8) {
     // =============================== softmax warpgroups =========================
     const int t = warp >> 2;                 // which 128-row tile
     const int wq = warp & 3;                 // TMEM lane quarter this warp may touch
@@ -241,6 +248,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int nt = n_t[t];
     const float c1 = a.c1, nc2 = -a.c2;
     float l = 0.f;
+    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // unmasked tiles accumulate here
 
     const bool tr_lane = (wq == 0 && lane == 0);
     for (int j = 0; j < nt; ++j) {
@@ -270,14 +278,21 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool need_mask = a.has_mask || (col0 + 127 >= a.Nk) ||
                              (a.causal && (col0 + 127 > m0 + 128 * t + off));
       if (!need_mask) {
+        // packed f32x2 math: one FFMA2 / FADD2 per element pair (halves the FMA-pipe instruction
+        // count next to the MUFU-bound exps); two independent row-sum chains per thread
+        const float2 c1v = make_float2(c1, c1), c2v = make_float2(nc2, nc2);
         auto chunk = [&](const uint32_t(&s)[32], int c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c1, nc2));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c1, nc2));
-            l += p0 + p1;
-            pk[i] = pack2<T>(p0, p1);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c1v, c2v);
+            // every kPolyEvery-th pair goes to the FMA pipe instead of the MUFU
+            const float2 pp = (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1)
+                                  ? ex2_poly2(x)
+                                  : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            if (i & 1) l2b = __fadd2_rn(l2b, pp);
+            else l2a = __fadd2_rn(l2a, pp);
+            pk[i] = pack2<T>(pp.x, pp.y);
           }
           if (c == 0) p_cols_free();
           tmem_st_x16(tP + c * 16, pk);
@@ -331,6 +346,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ---- epilogue: O * 1/max(l, eps) -> global ----------------------------------------
     // the clamp only guards rows with no visible key (l == 0, O == 0 -> o = 0; reference: cu:1239 uses
     // 1e-10, too large here because shift = scale*groups makes legitimately tiny row sums)
+    l += (l2a.x + l2a.y) + (l2b.x + l2b.y);
     const float inv = 1.0f / fmaxf(l, 1e-37f);
     const bool row_ok = row_g < a.Nq;
     T* orow = reinterpret_cast<T*>(a.o) + (long long)b * a.o_sb + (long long)h * a.o_sh +

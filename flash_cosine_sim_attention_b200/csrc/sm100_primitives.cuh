@@ -342,6 +342,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for a pair of x <= 0 on the FMA / ALU pipes (no MUFU): x = n + r with n = round(x),
+// r in [-0.5, 0.5]; cubic minimax for 2^r (max relative error 1.6e-4, below half an ulp of the
+// 16-bit P it feeds); the exponent is inserted with an integer shift-add.  The attention kernels
+// are MUFU-bound at head dim 64 (16384 exps vs 524 MMA cycles per 128x128 tile), so a fraction of
+// the exps is computed this way to unload the MUFU pipe.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));      // 1.5 * 2^23: low bits = round(x)
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(r, make_float2(5.676588789e-02f, 5.676588789e-02f), make_float2(2.427372634e-01f, 2.427372634e-01f));
+  p = __ffma2_rn(p, r, make_float2(6.929193139e-01f, 6.929193139e-01f));
+  p = __ffma2_rn(p, r, make_float2(9.999317527e-01f, 9.999317527e-01f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  y.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return y;
+}
+
 // pack two fp32 into one 32-bit word of 16-bit values, `lo` in bits [0,16)
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi);

@@ -241,6 +241,109 @@ __global__ void __launch_bounds__(512) probe_exp(float* out, int iters, int mode
 }
 
 // ------------------------------------------------------------------------------------
+// the forward softmax inner loop in isolation: per element FFMA + EX2 + FADD, per pair one F2FP
+//   mode 0: scalar math, registers only      mode 1: packed f32x2 math, registers only
+//   mode 2: mode 1 + tcgen05.ld of the 128 inputs and tcgen05.st of the 64 packed outputs per tile
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) probe_softmax_loop(float* out, int iters, int mode, long long* cycles) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 192;
+  const float c1 = 11.5f, nc2 = -11.5f;
+  float l = 0.f;
+  float2 l2 = make_float2(0.f, 0.f);
+  uint32_t sreg[4][32];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sreg[c][i] = __float_as_uint(0.001f * ((threadIdx.x * 7 + c * 32 + i) % 97));
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(lane_base + 32 * c, sreg[c]);
+      tmem_ld_wait();
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float p0, p1;
+        if (mode == 0) {
+          p0 = ex2_approx(fmaf(__uint_as_float(sreg[c][2 * i]), c1, nc2));
+          p1 = ex2_approx(fmaf(__uint_as_float(sreg[c][2 * i + 1]), c1, nc2));
+          l += p0 + p1;
+        } else {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sreg[c][2 * i]), __uint_as_float(sreg[c][2 * i + 1])),
+                                      make_float2(c1, c1), make_float2(nc2, nc2));
+          p0 = ex2_approx(x.x);
+          p1 = ex2_approx(x.y);
+          l2 = __fadd2_rn(l2, make_float2(p0, p1));
+        }
+        if (mode == 3) pk[i] = __float_as_uint(p0) ^ __float_as_uint(p1);          // no F2FP
+        else if (mode == 4) pk[i] = __float_as_uint(p0 + p1);                        // FADD instead of F2FP
+        else if (mode == 5) pk[i] = pack2<__half>(p0, p1);                             // f16 pack
+        else pk[i] = pack2<bf16>(p0, p1);
+      }
+      if (mode == 2) {
+        tmem_st_x16(lane_base + 128 + 16 * c, pk);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sreg[c][i] ^= (pk[i] & 1u);    // keep the packs alive, perturb the inputs
+      }
+    }
+    if (mode == 2) tmem_st_wait();
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = l + l2.x + l2.y;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// same math, but the body is ONE 32-element chunk executed 4x per tile from a rolled loop
+// (code footprint ~1/4): tests whether instruction fetch limits the fully unrolled version
+template <int UNROLL_CHUNKS>
+__global__ void __launch_bounds__(256) probe_softmax_rolled(float* out, int iters, long long* cycles) {
+  const float c1 = 11.5f, nc2 = -11.5f;
+  float2 l2 = make_float2(0.f, 0.f);
+  uint32_t sreg[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sreg[i] = __float_as_uint(0.001f * ((threadIdx.x * 7 + i) % 97));
+  long long t0 = clock64();
+#pragma unroll UNROLL_CHUNKS
+  for (int it = 0; it < iters * 4; ++it) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 x = __ffma2_rn(make_float2(__uint_as_float(sreg[2 * i]), __uint_as_float(sreg[2 * i + 1])),
+                                  make_float2(c1, c1), make_float2(nc2, nc2));
+      const float p0 = ex2_approx(x.x), p1 = ex2_approx(x.y);
+      l2 = __fadd2_rn(l2, make_float2(p0, p1));
+      pk[i] = pack2<bf16>(p0, p1);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      sreg[2 * i] ^= (pk[i] & 1u);
+      sreg[2 * i + 1] ^= ((pk[i] >> 16) & 1u);
+    }
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = l2.x + l2.y;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+// ------------------------------------------------------------------------------------
 // TMEM -> register bandwidth (tcgen05.ld 32x32b.x32), no tensor-pipe activity
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) probe_ldtm(float* out, int iters, int with_exp, long long* cycles) {
@@ -475,6 +578,41 @@ int main() {
       CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
       double per_clk = (double)iters * 8 * nthr / (double)cyc;
       printf("[RATE] %s : %.2f exp2 / clk / SM (%d warps/SM, dependent chains x8)\n", en[mode], per_clk, nthr / 32);
+    }
+  }
+  {
+    float* dE;
+    CK(cudaMalloc(&dE, 148 * 256 * 4));
+    const char* mm[6] = {"scalar FFMA/EX2/FADD + F2FP, registers only", "packed f32x2 math, registers only",
+                         "packed math + tcgen05.ld x128 / st x64 per tile", "packed math, XOR instead of F2FP",
+                         "packed math, FADD instead of F2FP", "packed math, f16 F2FP"};
+    for (int mode = 0; mode < 6; ++mode) {
+      const int iters = 256;
+      probe_softmax_loop<<<prop.multiProcessorCount, 256>>>(dE, iters, mode, dCyc);
+      CK(cudaDeviceSynchronize());
+      probe_softmax_loop<<<prop.multiProcessorCount, 256>>>(dE, iters, mode, dCyc);
+      CK(cudaDeviceSynchronize());
+      long long cyc;
+      CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
+      printf("[RATE] softmax loop, 8 warps/SM, %s: %.0f cycles per 128-element tile row-set (MUFU bound 2048 per 2 warps/SMSP), %.2f exp/clk/SM\n",
+             mm[mode], (double)cyc / iters, 256.0 * 128 * iters / cyc);
+    }
+  }
+  {
+    float* dE;
+    CK(cudaMalloc(&dE, 148 * 256 * 4));
+    const int iters = 256;
+    for (int v = 0; v < 3; ++v) {
+      for (int rep = 0; rep < 2; ++rep) {
+        if (v == 0) probe_softmax_rolled<1><<<prop.multiProcessorCount, 256>>>(dE, iters, dCyc);
+        if (v == 1) probe_softmax_rolled<4><<<prop.multiProcessorCount, 256>>>(dE, iters, dCyc);
+        if (v == 2) probe_softmax_rolled<16><<<prop.multiProcessorCount, 256>>>(dE, iters, dCyc);
+        CK(cudaDeviceSynchronize());
+      }
+      long long cyc;
+      CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
+      printf("[RATE] softmax loop rolled (unroll %d chunks of 32), 8 warps/SM: %.0f cycles per 128 elements, %.2f exp/clk/SM\n",
+             v == 0 ? 1 : (v == 1 ? 4 : 16), (double)cyc / iters, 256.0 * 128 * iters / cyc);
     }
   }
   // ---- TMEM read bandwidth ------------------------------------------------------------
