@@ -32,6 +32,10 @@
 
 #include <type_traits>
 
+#ifndef FCSA_BWD_POLY_EVERY
+#define FCSA_BWD_POLY_EVERY 3   // backward exp stage: 1 of every N exp pairs runs on the FMA pipe (0 = none)
+#endif
+
 #include "../../include/fcsa_b200.h"
 #include "l2norm_kernels.cuh"
 #include "sm100_primitives.cuh"
@@ -108,21 +112,19 @@ struct PrepArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
-  // D/8 threads per row, 16-byte loads, shuffle reduce
+  // grid = (row blocks of the padded sequence, batch*heads); D/8 threads per row, 16-byte loads,
+  // shuffle reduce.  No per-thread integer division on the address path.
   const int tpr = a.D >> 3;
   const int rows_per_block = 256 / tpr;
-  const long long prow = (long long)blockIdx.x * rows_per_block + threadIdx.x / tpr;  // padded row id
+  const int bh = blockIdx.y;
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int row = blockIdx.x * rows_per_block + threadIdx.x / tpr;     // row inside the padded (nqt*QT) range
   const int tr = threadIdx.x % tpr;
-  const long long padded = (long long)a.nqt * a.QT;
-  const long long total = (long long)a.B * a.H * padded;
-  const bool in = prow < total;
-  const long long pr = in ? prow : 0;
-  const int bh = (int)(pr / padded);
-  const int row = (int)(pr % padded);
-  const int b = bh / a.H, h = bh % a.H;
+  const int padded = a.nqt * a.QT;
+  const bool in = row < padded;
   const bool valid = in && row < a.Nq;
   if (in) {
-    uint4* z = reinterpret_cast<uint4*>(a.dq_acc) + (prow * tpr + tr) * 2;
+    uint4* z = reinterpret_cast<uint4*>(a.dq_acc) + (((long long)bh * padded + row) * tpr + tr) * 2;
     z[0] = make_uint4(0, 0, 0, 0);
     z[1] = make_uint4(0, 0, 0, 0);
   }
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
   }
   for (int m = 1; m < tpr; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
   if (in && tr == 0) {
-    const int qt = row / a.QT, r = row % a.QT;
+    const int qt = row / a.QT, r = row - qt * a.QT;
     float* st = a.stats + ((long long)bh * a.nqt + qt) * 2 * a.QT;
     float c3 = 0.f, dl = 0.f;
     if (valid) {
@@ -232,9 +234,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(BAR(KV_FULL), 1);
     for (int s = 0; s < NST; ++s) {
       mbar_init(BAR(Q_FULL + s), 1);
-      mbar_init(BAR(Q_EMPTY + s), 1);
+      mbar_init(BAR(Q_EMPTY + s), 2);
       mbar_init(BAR(DO_FULL + s), 1);
-      mbar_init(BAR(DO_EMPTY + s), 1);
+      mbar_init(BAR(DO_EMPTY + s), 2);
     }
     mbar_init(BAR(S_FULL), 1);
     mbar_init(BAR(S_FREE), 128);
@@ -246,7 +248,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(BAR(DS_FREE), 1);
     mbar_init(BAR(DQ_FULL), 1);
     mbar_init(BAR(DQ_EMPTY), 128);
-    mbar_init(BAR(DKV_FULL), 1);
+    mbar_init(BAR(DKV_FULL), 2);
     fence_mbar_init();
   }
   if (warp == 13) {
@@ -261,7 +263,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (wg == 3) {
     reg_dealloc<72>();
 #ifdef FCSA_TRACE
-    if (warp == 14 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
+    if (warp == 15 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
       // passive observer: when do the tensor-pipe results become visible?  (bounded spins: an
       // observer that falls two phases behind must not hang the kernel)
       auto watch = [&](int bar, uint32_t par) {
@@ -308,14 +310,15 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tma_load_4d(sDO + st * Cfg::kQ + ch * QCHUNK, &tm_do, BAR(DO_FULL + st), ch * 64, qt * QT, h, b);
         }
       }
-    } else if (warp == 13) {
-      // =============================== MMA issuer =================================
-      // Issue order per query tile i (it follows the order in which the inputs become ready, so the
-      // blocking waits never hold back work that could run):
-      //   S^T(i+1)   as soon as the exp warpgroup holds S^T(i) in registers
-      //   dV(i)      when P^T(i) is in the X columns
-      //   dK(i), dP^T(i+1), dQ(i)   when dS^T(i) is in TMEM / shared memory (dS^T aliases dP^T,
-      //              so dP^T(i+1) goes behind dK(i) in the in-order tensor pipe)
+    } else if (warp == 13 || warp == 14) {
+      // =============================== MMA issuers ================================
+      // Two issuing threads, one per dependency chain, so that neither waits behind the other's
+      // barriers (the tensor pipe interleaves the two instruction streams):
+      //   warp 13 (exp side): S^T(i+1) as soon as the exp warpgroup holds S^T(i) in registers;
+      //                       dV(i) += P^T(i) dO(i) when P^T(i) is in the X columns
+      //   warp 14 (dS side) : dK(i) += dS^T(i) Q(i), dP^T(i+1) (it overwrites dS^T(i), so it goes
+      //                       behind dK(i) in the in-order pipe), dQ(i)
+      // Q / dO ring slots are read by both chains: their empty barriers count 2.
       if (NI > 0 && elect_one()) {
         constexpr uint32_t idesc_s = umma_idesc<T>(128, QT, 0, 0);    // S^T, dP^T  (A, B K-major)
         constexpr uint32_t idesc_ts = umma_idesc<T>(128, D, 0, 1);    // dV, dK (A from TMEM, B MN-major)
@@ -330,72 +333,75 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     k > 0 ? 1u : 0u);
         };
         mbar_wait(BAR(KV_FULL), 0);
-        mbar_wait(BAR(Q_FULL + 0), 0);
-        tc_fence_after();
-        issue_ST(TM_S, sK, sQ);
-        umma_commit(BAR(S_FULL));
-        mbar_wait(BAR(DO_FULL + 0), 0);
-        tc_fence_after();
-        issue_ST(TM_DP, sV, sDO);
-        umma_commit(BAR(DP_FULL));
-
-        for (int i = 0; i < NI; ++i) {
-          const int st = i % NST, sn = (i + 1) % NST;
-          const uint32_t parn = ((i + 1) / NST) & 1;
-          const bool more = (i + 1 < NI);
-          // ---- S^T(i+1) ----
-          if (more) {
-            mbar_wait(BAR(S_FREE), i & 1);
-            mbar_wait(BAR(Q_FULL + sn), parn);
+        if (warp == 13) {
+          mbar_wait(BAR(Q_FULL + 0), 0);
+          tc_fence_after();
+          issue_ST(TM_S, sK, sQ);
+          umma_commit(BAR(S_FULL));
+          umma_commit(BAR(Q_EMPTY + 0));           // Q(0): this chain is done with it once S^T(0) completes
+          for (int i = 0; i < NI; ++i) {
+            const int st = i % NST, sn = (i + 1) % NST;
+            if (i + 1 < NI) {
+              mbar_wait(BAR(S_FREE), i & 1);
+              mbar_wait(BAR(Q_FULL + sn), ((i + 1) / NST) & 1);
+              tc_fence_after();
+              issue_ST(TM_S, sK, sQ + sn * Cfg::kQ);
+              umma_commit(BAR(S_FULL));
+              umma_commit(BAR(Q_EMPTY + sn));
+              FCSA_TR(0, i, 0);
+            }
+            mbar_wait(BAR(P_FULL), i & 1);
             tc_fence_after();
-            issue_ST(TM_S, sK, sQ + sn * Cfg::kQ);
-            umma_commit(BAR(S_FULL));
-            FCSA_TR(0, i, 0);
+#pragma unroll
+            for (int kk = 0; kk < QT / 16; ++kk)
+              umma_ts(tmem + TM_DV, tmem + TM_X + kk * 8,
+                      umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(BAR(PV_DONE));
+            umma_commit(BAR(DO_EMPTY + st));       // dO(i): this chain is done with it
+            FCSA_TR(0, i, 1);
           }
-          // ---- dV += P^T dO ----
-          mbar_wait(BAR(P_FULL), i & 1);
+          umma_commit(BAR(DKV_FULL));
+        } else {
+          mbar_wait(BAR(DO_FULL + 0), 0);
           tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < QT / 16; ++kk)
-            umma_ts(tmem + TM_DV, tmem + TM_X + kk * 8,
-                    umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
-                    (i > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(BAR(PV_DONE));
-          umma_commit(BAR(DO_EMPTY + st));
-          FCSA_TR(0, i, 1);
-          // ---- dK += dS^T Q ----
-          mbar_wait(BAR(DS_FULL), i & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < QT / 16; ++kk)
-            umma_ts(tmem + TM_DK, tmem + TM_DP + kk * 8,
-                    umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
-                    (i > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(BAR(Q_EMPTY + st));
-          FCSA_TR(0, i, 2);
-          // ---- dP^T(i+1) (overwrites dS^T(i): behind dK(i) in the pipe) ----
-          if (more) {
-            mbar_wait(BAR(DO_FULL + sn), parn);
+          issue_ST(TM_DP, sV, sDO);
+          umma_commit(BAR(DP_FULL));
+          umma_commit(BAR(DO_EMPTY + 0));
+          for (int i = 0; i < NI; ++i) {
+            const int st = i % NST, sn = (i + 1) % NST;
+            mbar_wait(BAR(DS_FULL), i & 1);
             tc_fence_after();
-            issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
-            umma_commit(BAR(DP_FULL));
-            FCSA_TR(0, i, 3);
-          }
-          // ---- dQ = dS K (D = 64) or dQ^T = K^T dS^T (D = 128): contraction over the 128 keys ----
-          mbar_wait(BAR(DQ_EMPTY), (i & 1) ^ 1);
-          tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t d_ds = umma_desc_sw128(sDS + kk * 2048, 16384, 1024);
-            const uint64_t d_k = umma_desc_sw128(sK + kk * 2048, 16384, 1024);
-            if (D == 64) umma_ss(tmem + TM_DQ, d_ds, d_k, idesc_dq, kk > 0 ? 1u : 0u);
-            else umma_ss(tmem + TM_DQ, d_k, d_ds, idesc_dq, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < QT / 16; ++kk)
+              umma_ts(tmem + TM_DK, tmem + TM_DP + kk * 8,
+                      umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(BAR(Q_EMPTY + st));
+            FCSA_TR(0, i, 2);
+            if (i + 1 < NI) {
+              mbar_wait(BAR(DO_FULL + sn), ((i + 1) / NST) & 1);
+              tc_fence_after();
+              issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
+              umma_commit(BAR(DP_FULL));
+              umma_commit(BAR(DO_EMPTY + sn));
+              FCSA_TR(0, i, 3);
+            }
+            mbar_wait(BAR(DQ_EMPTY), (i & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t d_ds = umma_desc_sw128(sDS + kk * 2048, 16384, 1024);
+              const uint64_t d_k = umma_desc_sw128(sK + kk * 2048, 16384, 1024);
+              if (D == 64) umma_ss(tmem + TM_DQ, d_ds, d_k, idesc_dq, kk > 0 ? 1u : 0u);
+              else umma_ss(tmem + TM_DQ, d_k, d_ds, idesc_dq, kk > 0 ? 1u : 0u);
+            }
+            umma_commit(BAR(DQ_FULL));
+            umma_commit(BAR(DS_FREE));
+            FCSA_TR(0, i, 4);
           }
-          umma_commit(BAR(DQ_FULL));
-          umma_commit(BAR(DS_FREE));
-          FCSA_TR(0, i, 4);
+          umma_commit(BAR(DKV_FULL));
         }
-        umma_commit(BAR(DKV_FULL));
       }
     }
   } else if (wg == 2) {
@@ -507,8 +513,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int e = 0; e < 32; e += 2) {
               const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c & 1][e]), __uint_as_float(s[c & 1][e + 1])),
                                           make_float2(c1, c1), make_float2(c3v[e], c3v[e + 1]));
-              float p0 = ex2_approx(x.x);
-              float p1 = ex2_approx(x.y);
+              // a third of the pairs on the FMA pipe: the exp warpgroup has the MUFU to itself but, one
+              // warp per scheduler, cannot keep it saturated and is the longest stage of the pipeline
+              const bool poly = FCSA_BWD_POLY_EVERY > 0 && ((e / 2) % (FCSA_BWD_POLY_EVERY > 0 ? FCSA_BWD_POLY_EVERY : 1)) == FCSA_BWD_POLY_EVERY - 1;
+              const float2 pe = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+              float p0 = pe.x;
+              float p1 = pe.y;
               if (MASKED) {
                 const int cc = 32 * c + e;
                 p0 = (cc >= lo && cc <= hi) ? p0 : 0.f;
@@ -567,6 +577,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
           }
           uint32_t pk[16];
+#ifdef FCSA_EXP_SKIP_DS_MATH
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = pp[c & 1][e] ^ d[c & 1][e];
+#else
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const float2 pa = unpack2<T>(pp[c & 1][e / 2]);
@@ -575,6 +589,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float2 ds = __fmul2_rn(pa, t);
             pk[e / 2] = pack2<T>(ds.x, ds.y);
           }
+#endif
           if (c == 0) {
             mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);        // the dQ product of tile i-1 has left smem dS
             if (tr_lane) FCSA_TR(2, i, 3);
@@ -583,10 +598,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_st_x16(tDP + 16 * c, pk);
           // the same 32 queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
           const int q0 = 32 * c;
+#ifndef FCSA_EXP_SKIP_STS
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
             sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), pk[4 * q4],
                    pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+#endif
         }
         tmem_st_wait();
         fence_proxy_async_smem();
@@ -752,15 +769,12 @@ __device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishA
 // One thread = 8 consecutive features of one row.
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs a) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)a.B * a.H * a.Nq * 8;
-  const bool ok = idx < total;
-  const long long id = ok ? idx : 0;
-  const int c8 = (int)(id & 7);
-  const long long rowid = id >> 3;
-  const int row = (int)(rowid % a.Nq);
-  const int bh = (int)(rowid / a.Nq);
-  const int b = bh / a.H, h = bh % a.H;
+  // grid = (blocks of 32 rows, batch*heads); 8 threads per row
+  const int bh = blockIdx.y;
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int c8 = threadIdx.x & 7;
+  const int row = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool ok = row < a.Nq;
   const int qt = row >> 7, r = row & 127, wq = r >> 5, rl = r & 31;
   const float* tile = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048;
   float g[8];
@@ -773,7 +787,7 @@ __global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs
     g[0] = lo.x * a.scale; g[1] = lo.y * a.scale; g[2] = lo.z * a.scale; g[3] = lo.w * a.scale;
     g[4] = hi.x * a.scale; g[5] = hi.y * a.scale; g[6] = hi.z * a.scale; g[7] = hi.w * a.scale;
   }
-  finish_l2norm_bwd<T>(g, a, ok, b, h, row, c8);
+  finish_l2norm_bwd<T>(g, a, ok, b, h, ok ? row : 0, c8);
   if (ok) {
     uint4 o4;
     o4.x = pack2<T>(g[0], g[1]);
@@ -902,9 +916,10 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     pa.d_o = h.d_o.ptr; pa.do_sb = h.d_o.sb; pa.do_sh = h.d_o.sh; pa.do_sn = h.d_o.sn;
     pa.inv_l = h.inv_l; pa.stats = stats; pa.dq_acc = dq_acc;
     const int rows_per_block = 256 / (D / 8);
-    const long long rows = (long long)h.B * h.H * w.nqt * Cfg::QT;
-    const long long grid = (rows + rows_per_block - 1) / rows_per_block;
-    bwd_prep_kernel<T><<<(unsigned)grid, 256, 0, stream>>>(pa);
+    const int padded = w.nqt * Cfg::QT;
+    dim3 grid((unsigned)((padded + rows_per_block - 1) / rows_per_block), (unsigned)(h.B * h.H));
+    if (h.B * h.H > 65535) { *err = "batch*heads > 65535 not supported"; return FCSA_ERR_INVALID; }
+    bwd_prep_kernel<T><<<grid, 256, 0, stream>>>(pa);
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = "backward preprocess launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
@@ -953,8 +968,8 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
     fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
     if (D == 64) {
-      const long long total = (long long)h.B * h.H * h.Nq * 8;
-      bwd_dq_finish64_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fa);
+      dim3 grid((unsigned)((h.Nq + 31) / 32), (unsigned)(h.B * h.H));
+      bwd_dq_finish64_kernel<T><<<grid, 256, 0, stream>>>(fa);
     } else {
       bwd_dq_finish128_kernel<T><<<(unsigned)((long long)h.B * h.H * w.nqt), 256, 0, stream>>>(fa);
     }

@@ -263,19 +263,20 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   float* rn[2] = {n->q_rnorm, n->k_rnorm};
   const int heads[2] = {p->heads, p->kv_heads};
   const int rows[2] = {p->seq_q, p->seq_k};
-  long long max_rows = 0;
+  int max_rows = 0, max_bh = 0;
   for (int t = 0; t < 2; ++t) {
     fcsa::L2Args& a = pa.t[t];
     a.B = p->batch; a.H = heads[t]; a.N = rows[t]; a.D = p->head_dim; a.G = n->groups;
     a.x_sb = src[t]->sb; a.x_sh = src[t]->sh; a.x_sn = src[t]->sn;
     a.y_sb = dst[t]->sb; a.y_sh = dst[t]->sh; a.y_sn = dst[t]->sn;
     a.x = src[t]->ptr; a.y = dst[t]->ptr; a.rnorm = rn[t];
-    const long long nr = (long long)a.B * a.H * a.N;
-    if (nr > max_rows) max_rows = nr;
+    if (a.N > max_rows) max_rows = a.N;
+    if (a.B * a.H > max_bh) max_bh = a.B * a.H;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int rows_per_block = 2 * (256 / (p->head_dim / 8));
-  dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), 2);
+  dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), (unsigned)max_bh, 2);
+  if (max_bh > 65535) return fail(FCSA_ERR_INVALID, "batch*heads > 65535 not supported by the l2norm launch");
   if (p->dtype == FCSA_BF16) fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(pa);
   else fcsa::l2norm_fwd_pair_kernel<__half><<<grid, 256, 0, s>>>(pa);
   cudaError_t e = cudaGetLastError();

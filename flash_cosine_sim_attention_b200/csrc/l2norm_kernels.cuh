@@ -90,33 +90,32 @@ struct L2PairArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
-  const L2Args& a = pa.t[blockIdx.y];
+  // grid = (row blocks, batch*heads, tensor): no per-thread integer division on the address path
+  const L2Args& a = pa.t[blockIdx.z];
+  const int bh = blockIdx.y;
+  if (bh >= a.B * a.H) return;                    // k may have fewer heads than q (block-uniform exit)
+  const int b = bh / a.H, h = bh - b * a.H;
   const int tpr = a.D >> 3;
   const int rows_per_block = 256 / tpr;
-  const long long total_rows = (long long)a.B * a.H * a.N;
   const int tr = threadIdx.x % tpr;
   const int gs = a.D / a.G;
-  long long row[2];
+  const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 8;
+  T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 8;
+  int nn[2];
   bool ok[2];
   uint4 raw[2];
-  const T* xp[2];
-  int bb[2], hh[2], nn[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    row[u] = ((long long)blockIdx.x * 2 + u) * rows_per_block + threadIdx.x / tpr;
-    ok[u] = row[u] < total_rows;
-    const long long rr = ok[u] ? row[u] : 0;
-    nn[u] = (int)(rr % a.N);
-    hh[u] = (int)((rr / a.N) % a.H);
-    bb[u] = (int)(rr / ((long long)a.N * a.H));
-    xp[u] = reinterpret_cast<const T*>(a.x) + bb[u] * a.x_sb + hh[u] * a.x_sh + nn[u] * a.x_sn + tr * 8;
+    nn[u] = (blockIdx.x * 2 + u) * rows_per_block + threadIdx.x / tpr;
+    ok[u] = nn[u] < a.N;
     raw[u] = make_uint4(0, 0, 0, 0);
   }
 #pragma unroll
   for (int u = 0; u < 2; ++u)
-    if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(xp[u]);
+    if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(xbase + (long long)nn[u] * a.x_sn);
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
+    const long long row = (long long)bh * a.N + nn[u];
     float f[8];
     {
       float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs p
       const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) rn[i] = r;
-      if (ok[u] && a.rnorm && (tr % tpg) == 0) a.rnorm[row[u] * a.G + tr / tpg] = r;
+      if (ok[u] && a.rnorm && (tr % tpg) == 0) a.rnorm[row * a.G + tr / tpg] = r;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) rn[i] = 0.f;
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs p
         for (int i = 0; i < gs; ++i) ss += f[g0 + i] * f[g0 + i];
         const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
         for (int i = 0; i < gs; ++i) rn[g0 + i] = r;
-        if (ok[u] && a.rnorm) a.rnorm[row[u] * a.G + (tr * 8 + g0) / gs] = r;
+        if (ok[u] && a.rnorm) a.rnorm[row * a.G + (tr * 8 + g0) / gs] = r;
       }
     }
     if (ok[u]) {
@@ -150,8 +149,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs p
       w.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
       w.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
       w.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
-      T* yp = reinterpret_cast<T*>(a.y) + bb[u] * a.y_sb + hh[u] * a.y_sh + nn[u] * a.y_sn + tr * 8;
-      *reinterpret_cast<uint4*>(yp) = w;
+      *reinterpret_cast<uint4*>(ybase + (long long)nn[u] * a.y_sn) = w;
     }
   }
 }
