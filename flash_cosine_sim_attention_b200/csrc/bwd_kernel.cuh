@@ -114,6 +114,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
   // grid = (row blocks of the padded sequence, batch*heads); D/8 threads per row, 16-byte loads,
   // shuffle reduce.  No per-thread integer division on the address path.
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = a.D >> 3;
   const int rows_per_block = 256 / tpr;
   const int bh = blockIdx.y;
@@ -201,13 +203,14 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   enum {
     KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
-    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, P_READ, PV_DONE, DP_FULL, DS_FULL, DS_FREE,
+    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, DS_FULL, DS_FREE,
     DQ_FULL, DQ_EMPTY, DKV_FULL, NBARS
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = warp >> 2;
+  pdl_launch_dependents();
 
   // ---- work item --------------------------------------------------------------------------
   const int bh_count = a.B * a.H;
@@ -239,12 +242,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(BAR(DO_EMPTY + s), 2);
     }
     mbar_init(BAR(S_FULL), 1);
-    mbar_init(BAR(S_FREE), 128);
-    mbar_init(BAR(P_FULL), 128);
-    mbar_init(BAR(P_READ), 128);
+    mbar_init(BAR(S_FREE), 256);
+    mbar_init(BAR(P_FULL), 256);
     mbar_init(BAR(PV_DONE), 1);
     mbar_init(BAR(DP_FULL), 1);
-    mbar_init(BAR(DS_FULL), 128);
+    mbar_init(BAR(DS_FULL), 256);
     mbar_init(BAR(DS_FREE), 1);
     mbar_init(BAR(DQ_FULL), 1);
     mbar_init(BAR(DQ_EMPTY), 128);
@@ -259,6 +261,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();          // stats / zeroed dq accumulator come from the preprocess kernel
 
   if (wg == 3) {
     reg_dealloc<72>();
@@ -332,6 +335,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         };
+        // packed dS^T of queries [16kk, 16kk+16): each compute warpgroup keeps its half inside its own
+        // QT/2 dP^T columns
+        auto ds_col = [](int kk) -> uint32_t {
+          constexpr int HQ = QT / 2;
+          const int w = (16 * kk) / HQ;
+          return static_cast<uint32_t>(w * HQ + (16 * kk - w * HQ) / 2);
+        };
         mbar_wait(BAR(KV_FULL), 0);
         if (warp == 13) {
           mbar_wait(BAR(Q_FULL + 0), 0);
@@ -374,7 +384,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < QT / 16; ++kk)
-              umma_ts(tmem + TM_DK, tmem + TM_DP + kk * 8,
+              umma_ts(tmem + TM_DK, tmem + TM_DP + ds_col(kk),
                       umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
                       (i > 0 || kk > 0) ? 1u : 0u);
             umma_commit(BAR(Q_EMPTY + st));
@@ -443,22 +453,27 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncwarp();
   } else {
     // =============================== compute warpgroups =============================
-    // Two-stage software pipeline over the query tiles, one stage per warpgroup, so that the
-    // MUFU-bound stage (exp) of tile i+1 overlaps the FMA-bound stage (dS) of tile i:
-    //   warpgroup 0: S^T -> P^T = exp2(S^T*c1 + c3)            -> X columns (packed 16 bit)
-    //   warpgroup 1: dP^T, P^T -> dS^T = P^T * (dP^T - delta)  -> over the dP^T columns it has
-    //                already consumed (packed 16 bit) and to shared memory
-    // Thread = key row.
+    // Both warpgroups run the SAME fused element-wise stage, each on one half of the query
+    // columns of every tile (thread = key row, warpgroup w owns columns [w*QT/2, (w+1)*QT/2)):
+    //   S^T -> P^T = exp2(S^T*c1 + c3)             -> X columns (packed 16 bit, A operand of dV)
+    //   dP^T, P^T (still in registers) -> dS^T = P^T * (dP^T - delta)
+    //                                              -> packed over the dP^T columns this warpgroup
+    //                                                 has consumed (A operand of dK) and to smem
+    // Splitting by columns instead of by stage halves the latency of each stage (two warps per
+    // scheduler work on the same tile) and P^T never makes a round trip through TMEM.
+    reg_alloc<176>();
     const int wq = warp & 3;
     const int r = wq * 32 + lane;            // key row inside the tile
     const int key_g = key0 + r;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t tX = lane_base + TM_X;
-    const bool tr_lane = (wq == 0 && lane == 0);
-
-    if (wg == 0) {
-      reg_alloc<200>();
-      const uint32_t tS = lane_base + TM_S;
+    constexpr int HQ = QT / 2;               // query columns per warpgroup
+    constexpr int NC = HQ / 32;              // chunks of 32 columns
+    const int cq0 = wg * HQ;
+    const uint32_t tS = lane_base + TM_S + cq0;
+    const uint32_t tDP = lane_base + TM_DP + cq0;
+    const uint32_t tX = lane_base + TM_X + cq0 / 2;
+    const bool tr_lane = (wg == 0 && wq == 0 && lane == 0);
+    {
       const float c1 = a.c1;
       bool key_ok = key_g < a.Nk;
       if (a.has_mask && key_ok) key_ok = a.mask[(long long)b * a.mask_sb + key_g] != 0;
@@ -467,7 +482,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int i = 0; i < NI; ++i) {
         const int st = i % NST, qt = i_lo + i;
         const int row0 = qt * QT;
-        const uint32_t c3a = sStats + st * 1024;
+        const uint32_t c3a = sStats + st * 1024 + cq0 * 4;           // c3 of this warpgroup's queries
+        const uint32_t dla = sStats + st * 1024 + (QT + cq0) * 4;    // -delta of the same
         // visible iff lo <= cc <= hi  (cc = query index inside the tile)
         const bool need_mask = tile_key_ragged || (row0 + QT - 1 >= a.Nq) ||
                                (a.causal && (key0 + 127 > row0 + off));
@@ -478,31 +494,27 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (!key_ok) lo = 1000;
         }
         if (tr_lane) FCSA_TR(1, i, 0);
-        mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // c3 of this tile is in smem
+        mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // c3 / delta of this tile are in smem
         mbar_wait(BAR(S_FULL), i & 1);
         if (tr_lane) FCSA_TR(1, i, 1);
         tc_fence_after();
-        // Chunks of 32 query columns, the TMEM load of chunk c+1 in flight under the math of
-        // chunk c.  All shared-memory operands of a chunk are fetched in one batch first so the
-        // exp chain (FFMA -> MUFU -> pack) of 32 independent elements can be pipelined freely.
-        // The masked variant is a separate instantiation: a per-element `if (need_mask)` compiles
-        // to a taken branch per element pair and starves the warp of instructions.
-        constexpr int NC = QT / 32;
-        uint32_t pk[NC][16];
+        // ---- exp stage.  All TMEM loads of the half tile are issued up front; the shared-memory
+        // operands of a chunk are fetched in one batch so the exp chain (FFMA -> MUFU -> pack) of
+        // 32 independent elements can be pipelined freely.  The masked variant is a separate
+        // instantiation: a per-element `if (need_mask)` compiles to a taken branch per element
+        // pair and starves the warp of instructions.
+        uint32_t pk[NC][16];                 // P^T packed; lives until the dS stage below
+        uint32_t s[NC][32];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_ld_x32(tS + 32 * c, s[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(BAR(S_FREE));                         // S^T(i+1) may be produced now
+        if (tr_lane) FCSA_TR(1, i, 2);
         auto exp_tile = [&](auto masked_tag) {
           constexpr bool MASKED = decltype(masked_tag)::value;
-          uint32_t s[2][32];
-          tmem_ld_x32(tS, s[0]);
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            tmem_ld_wait();
-            if (c + 1 < NC) {
-              tmem_ld_x32(tS + 32 * (c + 1), s[(c + 1) & 1]);
-            } else {
-              tc_fence_before();
-              mbar_arrive(BAR(S_FREE));                   // S^T(i+1) may be produced now
-              if (tr_lane) FCSA_TR(1, i, 2);
-            }
             float c3v[32];
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
@@ -511,16 +523,15 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
-              const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c & 1][e]), __uint_as_float(s[c & 1][e + 1])),
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][e]), __uint_as_float(s[c][e + 1])),
                                           make_float2(c1, c1), make_float2(c3v[e], c3v[e + 1]));
-              // a third of the pairs on the FMA pipe: the exp warpgroup has the MUFU to itself but, one
-              // warp per scheduler, cannot keep it saturated and is the longest stage of the pipeline
+              // some of the pairs on the FMA pipe (cubic minimax exp2), the rest on the MUFU
               const bool poly = FCSA_BWD_POLY_EVERY > 0 && ((e / 2) % (FCSA_BWD_POLY_EVERY > 0 ? FCSA_BWD_POLY_EVERY : 1)) == FCSA_BWD_POLY_EVERY - 1;
               const float2 pe = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
               float p0 = pe.x;
               float p1 = pe.y;
               if (MASKED) {
-                const int cc = 32 * c + e;
+                const int cc = cq0 + 32 * c + e;
                 p0 = (cc >= lo && cc <= hi) ? p0 : 0.f;
                 p1 = (cc + 1 >= lo && cc + 1 <= hi) ? p1 : 0.f;
               }
@@ -531,85 +542,59 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (need_mask) exp_tile(std::true_type{});
         else exp_tile(std::false_type{});
         if (tr_lane) FCSA_TR(1, i, 3);
-        // X still holds P^T(i-1): dV(i-1) and the dS warpgroup must be done reading it
-        if (i > 0) {
-          mbar_wait(BAR(PV_DONE), (i - 1) & 1);
-          mbar_wait(BAR(P_READ), (i - 1) & 1);
-        }
+        // X still holds P^T(i-1) until dV(i-1) has read it
+        if (i > 0) mbar_wait(BAR(PV_DONE), (i - 1) & 1);
 #pragma unroll
         for (int c = 0; c < NC; ++c) tmem_st_x16(tX + 16 * c, pk[c]);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(BAR(P_FULL));
         if (tr_lane) FCSA_TR(1, i, 4);
-      }
-    } else {
-      reg_alloc<152>();
-      const uint32_t tDP = lane_base + TM_DP;
-      for (int i = 0; i < NI; ++i) {
-        const int st = i % NST;
-        const uint32_t dla = sStats + st * 1024 + QT * 4;       // delta of this tile's queries
-        if (tr_lane) FCSA_TR(2, i, 0);
-        mbar_wait(BAR(P_FULL), i & 1);
-        if (tr_lane) FCSA_TR(2, i, 1);
-        mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);
+
+        // ---- dS stage
         mbar_wait(BAR(DP_FULL), i & 1);
-        if (tr_lane) FCSA_TR(2, i, 2);
+        if (tr_lane) FCSA_TR(2, i, 0);
         tc_fence_after();
-        constexpr int NC = QT / 32;
-        uint32_t d[2][32], pp[2][16];
-        tmem_ld_x32(tDP, d[0]);
-        tmem_ld_x16(tX, pp[0]);
+        uint32_t (&d)[NC][32] = s;            // the S^T registers are dead: reuse them for dP^T
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_ld_x32(tDP + 32 * c, d[c]);
+        tmem_ld_wait();
+        if (tr_lane) FCSA_TR(2, i, 1);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < NC) {                                // prefetch the next chunk
-            tmem_ld_x32(tDP + 32 * (c + 1), d[(c + 1) & 1]);
-            tmem_ld_x16(tX + 16 * (c + 1), pp[(c + 1) & 1]);
-          } else {
-            tc_fence_before();
-            mbar_arrive(BAR(P_READ));                      // X may take P^T(i+1) (once dV(i) is done too)
-          }
           float dlv[32];
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 dl = lds128f(dla + (32 * c + e) * 4);
             dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
           }
-          uint32_t pk[16];
-#ifdef FCSA_EXP_SKIP_DS_MATH
-#pragma unroll
-          for (int e = 0; e < 16; ++e) pk[e] = pp[c & 1][e] ^ d[c & 1][e];
-#else
+          uint32_t ds[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float2 pa = unpack2<T>(pp[c & 1][e / 2]);
-            const float2 t = __fadd2_rn(make_float2(__uint_as_float(d[c & 1][e]), __uint_as_float(d[c & 1][e + 1])),
+            const float2 pa = unpack2<T>(pk[c][e / 2]);
+            const float2 t = __fadd2_rn(make_float2(__uint_as_float(d[c][e]), __uint_as_float(d[c][e + 1])),
                                         make_float2(dlv[e], dlv[e + 1]));        // dP - delta (delta stored negated)
-            const float2 ds = __fmul2_rn(pa, t);
-            pk[e / 2] = pack2<T>(ds.x, ds.y);
+            const float2 v = __fmul2_rn(pa, t);
+            ds[e / 2] = pack2<T>(v.x, v.y);
           }
-#endif
           if (c == 0) {
             mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);        // the dQ product of tile i-1 has left smem dS
-            if (tr_lane) FCSA_TR(2, i, 3);
+            if (tr_lane) FCSA_TR(2, i, 2);
           }
-          // packed dS^T over dP^T columns [16c, 16c+16) - all inside chunks this thread has loaded
-          tmem_st_x16(tDP + 16 * c, pk);
+          // packed dS^T over dP^T columns [cq0 + 16c, cq0 + 16c + 16): inside what this warpgroup has loaded
+          tmem_st_x16(tDP + 16 * c, ds);
           // the same 32 queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
-          const int q0 = 32 * c;
-#ifndef FCSA_EXP_SKIP_STS
+          const int q0 = cq0 + 32 * c;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
-            sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), pk[4 * q4],
-                   pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-#endif
+            sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), ds[4 * q4],
+                   ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]);
         }
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(BAR(DS_FULL));
-        if (tr_lane) FCSA_TR(2, i, 4);
+        if (tr_lane) FCSA_TR(2, i, 3);
       }
     }
 
@@ -770,6 +755,8 @@ __device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishA
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs a) {
   // grid = (blocks of 32 rows, batch*heads); 8 threads per row
+  pdl_launch_dependents();
+  pdl_wait();
   const int bh = blockIdx.y;
   const int b = bh / a.H, h = bh - b * a.H;
   const int c8 = threadIdx.x & 7;
@@ -804,6 +791,8 @@ __global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArgs a) {
   __shared__ float tile[64][129];
+  pdl_launch_dependents();
+  pdl_wait();
   const long long unit = blockIdx.x;                       // (bh, qt)
   const int qt = (int)(unit % a.nqt);
   const int bh = (int)(unit / a.nqt);
@@ -919,8 +908,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     const int padded = w.nqt * Cfg::QT;
     dim3 grid((unsigned)((padded + rows_per_block - 1) / rows_per_block), (unsigned)(h.B * h.H));
     if (h.B * h.H > 65535) { *err = "batch*heads > 65535 not supported"; return FCSA_ERR_INVALID; }
-    bwd_prep_kernel<T><<<grid, 256, 0, stream>>>(pa);
-    e = cudaGetLastError();
+    e = launch_pdl(bwd_prep_kernel<T>, grid, dim3(256), 0, stream, pa);
     if (e != cudaSuccess) { *err = "backward preprocess launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
   }
@@ -954,8 +942,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     }
     const long long grid = (long long)((h.Nk + 127) / 128) * h.B * h.H;
     if (h.ev_start) cudaEventRecord(h.ev_start, stream);
-    kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(tq, tk, tv, tdo, a);
-    e = cudaGetLastError();
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, tdo, a);
     if (h.ev_stop) cudaEventRecord(h.ev_stop, stream);
     if (e != cudaSuccess) { *err = "backward kernel launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
@@ -969,11 +956,10 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
     if (D == 64) {
       dim3 grid((unsigned)((h.Nq + 31) / 32), (unsigned)(h.B * h.H));
-      bwd_dq_finish64_kernel<T><<<grid, 256, 0, stream>>>(fa);
+      e = launch_pdl(bwd_dq_finish64_kernel<T>, grid, dim3(256), 0, stream, fa);
     } else {
-      bwd_dq_finish128_kernel<T><<<(unsigned)((long long)h.B * h.H * w.nqt), 256, 0, stream>>>(fa);
+      e = launch_pdl(bwd_dq_finish128_kernel<T>, dim3((unsigned)((long long)h.B * h.H * w.nqt)), dim3(256), 0, stream, fa);
     }
-    e = cudaGetLastError();
     if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
     if (shared_kv) {

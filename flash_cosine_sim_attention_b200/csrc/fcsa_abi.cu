@@ -112,8 +112,7 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
   const long long grid = (long long)a.n_qblk * p->batch * p->heads;
   if (grid > 0x7FFFFFFFLL) return fail(FCSA_ERR_INVALID, "problem too large for one launch");
   if (g_ev[0][0]) cudaEventRecord(g_ev[0][0], stream);
-  kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(tq, tk, tv, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = fcsa::launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, a);
   if (g_ev[0][1]) cudaEventRecord(g_ev[0][1], stream);
   if (e != cudaSuccess) return cuda_fail(e, "forward kernel launch");
   g_launches.fetch_add(1);
@@ -277,9 +276,9 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   const int rows_per_block = 2 * (256 / (p->head_dim / 8));
   dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), (unsigned)max_bh, 2);
   if (max_bh > 65535) return fail(FCSA_ERR_INVALID, "batch*heads > 65535 not supported by the l2norm launch");
-  if (p->dtype == FCSA_BF16) fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(pa);
-  else fcsa::l2norm_fwd_pair_kernel<__half><<<grid, 256, 0, s>>>(pa);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = (p->dtype == FCSA_BF16)
+                      ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, pa)
+                      : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half>, grid, dim3(256), 0, s, pa);
   if (e != cudaSuccess) return cuda_fail(e, "l2norm (q, k) launch");
   g_launches.fetch_add(1);
   return fcsa_forward(p, &n->q_hat, &n->k_hat, v, o, inv_l, stream);

@@ -82,6 +82,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // ---- which work item ---------------------------------------------------------------
   const int bh_count = a.B * a.H;
@@ -140,6 +141,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();          // q, k (normalised by the previous kernel), v, mask are read from here on
 
   if (warp == 8) {
     // =============================== TMA producer ===============================

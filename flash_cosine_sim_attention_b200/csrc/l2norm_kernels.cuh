@@ -91,6 +91,8 @@ struct L2PairArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
   // grid = (row blocks, batch*heads, tensor): no per-thread integer division on the address path
+  pdl_launch_dependents();
+  pdl_wait();
   const L2Args& a = pa.t[blockIdx.z];
   const int bh = blockIdx.y;
   if (bh >= a.B * a.H) return;                    // k may have fewer heads than q (block-uniform exit)

@@ -120,6 +120,20 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
+// Programmatic dependent launch: every kernel of a step is launched with the
+// programmatic-stream-serialization attribute.  `pdl_launch_dependents` (first thing in a kernel)
+// lets the next kernel of the stream start being scheduled as soon as all CTAs of this one have
+// started; `pdl_wait` blocks until the previous kernel has completed and its writes are visible -
+// it must precede the first access to global memory that kernel may have produced.  Between the
+// two a kernel runs its private prologue (barrier init, TMEM allocation, descriptor prefetch),
+// which thereby overlaps the previous kernel's tail instead of adding to the launch gap.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
   long long t0 = tr[1][0][0];
   const char* names[6] = {"MMA  [S(i+1) issued, dV issued, dK issued, dP(i+1) issued, dQ issued]",
                           "EXP  [top, S_FULL seen, S in regs, exps done, P arrived]",
-                          "DS   [top, P loaded, DP_FULL seen, DS_FREE ok, DS arrived]",
+                          "DS   [DP_FULL seen, dP in regs, DS_FREE ok, DS arrived, -]",
                           "RED  [DQ_FULL seen, reduce issued]",
                           "TMA  [Q_EMPTY seen, DO_EMPTY seen]", "OBS  [S_FULL, DP_FULL, PV_DONE, DQ_FULL complete]"};
   int nslots[6] = {5, 5, 5, 2, 2, 4};
