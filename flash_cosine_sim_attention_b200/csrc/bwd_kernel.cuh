@@ -59,7 +59,7 @@ struct BwdCfg {
   static constexpr int kOffStats = kOffDQ + 32768;        // NST stages x 1 KB (2*QT floats used)
   static constexpr int kOffBar = kOffStats + NST * 1024;
   static constexpr int kSmem = kOffBar + 256 + 1024;
-  static constexpr int kThreads = 512;
+  static constexpr int kThreads = 640;                  // 16 compute warps + 4 service warps
   // TMEM columns
   static constexpr uint32_t TM_S = 0, TM_DP = QT, TM_DV = 2 * QT, TM_DK = 2 * QT + D, TM_DQ = 2 * QT + 2 * D,
                             TM_X = 2 * QT + 2 * D + 64;   // QT/2 columns of packed P^T, then dS^T
@@ -175,7 +175,7 @@ struct BwdArgs {
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(640, 1)
 fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const BwdArgs a) {
@@ -229,7 +229,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int NI = a.nqt - i_lo;                          // number of query tiles to visit (>= 1)
 
   // ---- setup ------------------------------------------------------------------------------
-  if (warp == 12 && elect_one()) {
+  if (warp == 16 && elect_one()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -242,18 +242,18 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(BAR(DO_EMPTY + s), 2);
     }
     mbar_init(BAR(S_FULL), 1);
-    mbar_init(BAR(S_FREE), 256);
-    mbar_init(BAR(P_FULL), 256);
+    mbar_init(BAR(S_FREE), 512);
+    mbar_init(BAR(P_FULL), 512);
     mbar_init(BAR(PV_DONE), 1);
     mbar_init(BAR(DP_FULL), 1);
-    mbar_init(BAR(DS_FULL), 256);
+    mbar_init(BAR(DS_FULL), 512);
     mbar_init(BAR(DS_FREE), 1);
     mbar_init(BAR(DQ_FULL), 1);
-    mbar_init(BAR(DQ_EMPTY), 128);
+    mbar_init(BAR(DQ_EMPTY), 512);
     mbar_init(BAR(DKV_FULL), 2);
     fence_mbar_init();
   }
-  if (warp == 13) {
+  if (warp == 17) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
@@ -263,10 +263,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
   pdl_wait();          // stats / zeroed dq accumulator come from the preprocess kernel
 
-  if (wg == 3) {
-    reg_dealloc<72>();
+  if (wg == 4) {
+    reg_dealloc<64>();
 #ifdef FCSA_TRACE
-    if (warp == 15 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
+    if (warp == 19 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
       // passive observer: when do the tensor-pipe results become visible?  (bounded spins: an
       // observer that falls two phases behind must not hang the kernel)
       auto watch = [&](int bar, uint32_t par) {
@@ -285,7 +285,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
 #endif
-    if (warp == 12) {
+    if (warp == 16) {
       // =============================== TMA producer ===============================
       if (NI > 0 && elect_one()) {
         mbar_expect_tx(BAR(KV_FULL), 2 * Cfg::kKV);
@@ -313,7 +313,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tma_load_4d(sDO + st * Cfg::kQ + ch * QCHUNK, &tm_do, BAR(DO_FULL + st), ch * 64, qt * QT, h, b);
         }
       }
-    } else if (warp == 13 || warp == 14) {
+    } else if (warp == 17 || warp == 18) {
       // =============================== MMA issuers ================================
       // Two issuing threads, one per dependency chain, so that neither waits behind the other's
       // barriers (the tensor pipe interleaves the two instruction streams):
@@ -335,15 +335,15 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         };
-        // packed dS^T of queries [16kk, 16kk+16): each compute warpgroup keeps its half inside its own
-        // QT/2 dP^T columns
+        // packed dS^T of queries [16kk, 16kk+16): each compute warpgroup keeps its quarter inside its
+        // own QT/4 dP^T columns
         auto ds_col = [](int kk) -> uint32_t {
-          constexpr int HQ = QT / 2;
-          const int w = (16 * kk) / HQ;
-          return static_cast<uint32_t>(w * HQ + (16 * kk - w * HQ) / 2);
+          constexpr int CW = QT / 4;
+          const int w = (16 * kk) / CW;
+          return static_cast<uint32_t>(w * CW + (16 * kk - w * CW) / 2);
         };
         mbar_wait(BAR(KV_FULL), 0);
-        if (warp == 13) {
+        if (warp == 17) {
           mbar_wait(BAR(Q_FULL + 0), 0);
           tc_fence_after();
           issue_ST(TM_S, sK, sQ);
@@ -400,6 +400,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(BAR(DQ_EMPTY), (i & 1) ^ 1);
             tc_fence_after();
 #pragma unroll
+#ifdef FCSA_EXP_NO_DQMMA
+            if (false)
+#endif
             for (int kk = 0; kk < 8; ++kk) {
               const uint64_t d_ds = umma_desc_sw128(sDS + kk * 2048, 16384, 1024);
               const uint64_t d_k = umma_desc_sw128(sK + kk * 2048, 16384, 1024);
@@ -414,20 +417,50 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-  } else if (wg == 2) {
-    // =============================== dQ reduce warpgroup ============================
-    reg_dealloc<88>();
+  } else {
+    // =============================== compute warpgroups =============================
+    // Four warpgroups run the SAME fused element-wise stage, each on one quarter of the query
+    // columns of every tile (thread = key row, warpgroup g owns columns [g*QT/4, (g+1)*QT/4)):
+    //   S^T -> P^T = exp2(S^T*c1 + c3)             -> X columns (packed 16 bit, A operand of dV)
+    //   dP^T, P^T (still in registers) -> dS^T = P^T * (dP^T - delta)
+    //                                              -> packed over the dP^T columns this warpgroup
+    //                                                 has consumed (A operand of dK) and to smem
+    //   dQ(i-1) partial tile: 16 accumulator columns -> smem -> TMA bulk reduce-add (2 KB per warp)
+    // Splitting by columns (not by stage) puts four warps on every scheduler, all working on the
+    // same tile: the TMEM / MUFU / shared-memory latencies of one warp hide under the others, and
+    // P^T never makes a round trip through TMEM.
+    reg_alloc<104>();   // 4 x 104 + 64 = 5 x 96: the pool is what the CTA was launched with (640 x 96)
     const int wq = warp & 3;
+    const int r = wq * 32 + lane;            // key row inside the tile
+    const int key_g = key0 + r;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_stage = sDQ + wq * 8192;                  // 8 KB per warp
-    for (int i = 0; i < NI; ++i) {
-      const int qt = i_lo + i;
-      mbar_wait(BAR(DQ_FULL), i & 1);
-      if (warp == 8 && lane == 0) FCSA_TR(3, i, 0);
+    constexpr int CW = QT / 4;               // query columns per warpgroup (32 or 16)
+    const int cq0 = wg * CW;
+    const uint32_t tS = lane_base + TM_S + cq0;
+    const uint32_t tDP = lane_base + TM_DP + cq0;
+    const uint32_t tX = lane_base + TM_X + cq0 / 2;
+    const uint32_t tDQ = lane_base + TM_DQ + 16 * wg;
+    const uint32_t my_stage = sDQ + wq * 8192 + wg * 2048;     // 2 KB of dQ staging per warp
+    const bool tr_lane = (wg == 0 && wq == 0 && lane == 0);
+    auto ld_cw = [&](uint32_t addr, uint32_t (&dst)[CW]) {
+      if constexpr (CW == 32) tmem_ld_x32(addr, dst);
+      else tmem_ld_x16(addr, dst);
+    };
+    auto st_cw = [&](uint32_t addr, const uint32_t (&src)[CW / 2]) {
+      if constexpr (CW == 32) tmem_st_x16(addr, src);
+      else tmem_st_x8(addr, src);
+    };
+    // dQ of tile j: this warp's 32 rows x 16 accumulator columns
+    auto drain_dq = [&](int j) {
+      mbar_wait(BAR(DQ_FULL), j & 1);
+      if (tr_lane) FCSA_TR(3, j, 0);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_x32(lane_base + TM_DQ, r0);
-      tmem_ld_x32(lane_base + TM_DQ + 32, r1);
+#ifdef FCSA_EXP_NO_DRAIN
+      mbar_arrive(BAR(DQ_EMPTY));
+      return;
+#endif
+      uint32_t q[16];
+      tmem_ld_x16(tDQ, q);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(BAR(DQ_EMPTY));
@@ -435,44 +468,21 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        sts128(my_stage + c * 512 + lane * 16, r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        sts128(my_stage + (8 + c) * 512 + lane * 16, r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        sts128(my_stage + c * 512 + lane * 16, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+#ifndef FCSA_EXP_SKIP_DRAIN_FENCE
       fence_proxy_async_smem();
+#endif
       __syncwarp();
+#ifndef FCSA_EXP_SKIP_REDUCE
       if (lane == 0) {
-        float* dst = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048;
-        bulk_reduce_add_f32(dst, my_stage, 8192);
+        float* dst = a.dq_acc + (((long long)bh * a.nqt + (i_lo + j)) * 4 + wq) * 2048 + wg * 512;
+        bulk_reduce_add_f32(dst, my_stage, 2048);
         bulk_commit_group();
       }
-      if (warp == 8 && lane == 0) FCSA_TR(3, i, 1);
-    }
-    if (lane == 0) bulk_wait_group<0>();
-    __syncwarp();
-  } else {
-    // =============================== compute warpgroups =============================
-    // Both warpgroups run the SAME fused element-wise stage, each on one half of the query
-    // columns of every tile (thread = key row, warpgroup w owns columns [w*QT/2, (w+1)*QT/2)):
-    //   S^T -> P^T = exp2(S^T*c1 + c3)             -> X columns (packed 16 bit, A operand of dV)
-    //   dP^T, P^T (still in registers) -> dS^T = P^T * (dP^T - delta)
-    //                                              -> packed over the dP^T columns this warpgroup
-    //                                                 has consumed (A operand of dK) and to smem
-    // Splitting by columns instead of by stage halves the latency of each stage (two warps per
-    // scheduler work on the same tile) and P^T never makes a round trip through TMEM.
-    reg_alloc<176>();
-    const int wq = warp & 3;
-    const int r = wq * 32 + lane;            // key row inside the tile
-    const int key_g = key0 + r;
-    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    constexpr int HQ = QT / 2;               // query columns per warpgroup
-    constexpr int NC = HQ / 32;              // chunks of 32 columns
-    const int cq0 = wg * HQ;
-    const uint32_t tS = lane_base + TM_S + cq0;
-    const uint32_t tDP = lane_base + TM_DP + cq0;
-    const uint32_t tX = lane_base + TM_X + cq0 / 2;
-    const bool tr_lane = (wg == 0 && wq == 0 && lane == 0);
+#endif
+      if (tr_lane) FCSA_TR(3, j, 1);
+    };
     {
       const float c1 = a.c1;
       bool key_ok = key_g < a.Nk;
@@ -498,15 +508,19 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(BAR(S_FULL), i & 1);
         if (tr_lane) FCSA_TR(1, i, 1);
         tc_fence_after();
-        // ---- exp stage.  All TMEM loads of the half tile are issued up front; the shared-memory
-        // operands of a chunk are fetched in one batch so the exp chain (FFMA -> MUFU -> pack) of
-        // 32 independent elements can be pipelined freely.  The masked variant is a separate
-        // instantiation: a per-element `if (need_mask)` compiles to a taken branch per element
-        // pair and starves the warp of instructions.
-        uint32_t pk[NC][16];                 // P^T packed; lives until the dS stage below
-        uint32_t s[NC][32];
+        // ---- exp stage.  The shared-memory operands are fetched in one batch so the exp chain
+        // (FFMA -> MUFU -> pack) of CW independent elements can be pipelined freely.  The masked
+        // variant is a separate instantiation: a per-element `if (need_mask)` compiles to a taken
+        // branch per element pair and starves the warp of instructions.
+        uint32_t pk[CW / 2];                 // P^T packed; lives until the dS stage below
+        uint32_t s[CW];
+        ld_cw(tS, s);
+        float c3v[CW];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) tmem_ld_x32(tS + 32 * c, s[c]);
+        for (int e = 0; e < CW; e += 4) {
+          const float4 k0 = lds128f(c3a + e * 4);
+          c3v[e] = k0.x; c3v[e + 1] = k0.y; c3v[e + 2] = k0.z; c3v[e + 3] = k0.w;
+        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(BAR(S_FREE));                         // S^T(i+1) may be produced now
@@ -514,29 +528,24 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         auto exp_tile = [&](auto masked_tag) {
           constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            float c3v[32];
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 k0 = lds128f(c3a + (32 * c + e) * 4);
-              c3v[e] = k0.x; c3v[e + 1] = k0.y; c3v[e + 2] = k0.z; c3v[e + 3] = k0.w;
+          for (int e = 0; e < CW; e += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])),
+                                        make_float2(c1, c1), make_float2(c3v[e], c3v[e + 1]));
+            // some of the pairs on the FMA pipe (cubic minimax exp2), the rest on the MUFU
+            const bool poly = FCSA_BWD_POLY_EVERY > 0 && ((e / 2) % (FCSA_BWD_POLY_EVERY > 0 ? FCSA_BWD_POLY_EVERY : 1)) == FCSA_BWD_POLY_EVERY - 1;
+#ifdef FCSA_EXP_NO_EXP
+            const float2 pe = x;
+#else
+            const float2 pe = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+#endif
+            float p0 = pe.x;
+            float p1 = pe.y;
+            if (MASKED) {
+              const int cc = cq0 + e;
+              p0 = (cc >= lo && cc <= hi) ? p0 : 0.f;
+              p1 = (cc + 1 >= lo && cc + 1 <= hi) ? p1 : 0.f;
             }
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][e]), __uint_as_float(s[c][e + 1])),
-                                          make_float2(c1, c1), make_float2(c3v[e], c3v[e + 1]));
-              // some of the pairs on the FMA pipe (cubic minimax exp2), the rest on the MUFU
-              const bool poly = FCSA_BWD_POLY_EVERY > 0 && ((e / 2) % (FCSA_BWD_POLY_EVERY > 0 ? FCSA_BWD_POLY_EVERY : 1)) == FCSA_BWD_POLY_EVERY - 1;
-              const float2 pe = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-              float p0 = pe.x;
-              float p1 = pe.y;
-              if (MASKED) {
-                const int cc = cq0 + 32 * c + e;
-                p0 = (cc >= lo && cc <= hi) ? p0 : 0.f;
-                p1 = (cc + 1 >= lo && cc + 1 <= hi) ? p1 : 0.f;
-              }
-              pk[c][e / 2] = pack2<T>(p0, p1);
-            }
+            pk[e / 2] = pack2<T>(p0, p1);
           }
         };
         if (need_mask) exp_tile(std::true_type{});
@@ -544,61 +553,67 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr_lane) FCSA_TR(1, i, 3);
         // X still holds P^T(i-1) until dV(i-1) has read it
         if (i > 0) mbar_wait(BAR(PV_DONE), (i - 1) & 1);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) tmem_st_x16(tX + 16 * c, pk[c]);
+        st_cw(tX, pk);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(BAR(P_FULL));
         if (tr_lane) FCSA_TR(1, i, 4);
 
         // ---- dS stage
+        float dlv[CW];
+#pragma unroll
+        for (int e = 0; e < CW; e += 4) {
+          const float4 dl = lds128f(dla + e * 4);
+          dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
+        }
         mbar_wait(BAR(DP_FULL), i & 1);
         if (tr_lane) FCSA_TR(2, i, 0);
         tc_fence_after();
-        uint32_t (&d)[NC][32] = s;            // the S^T registers are dead: reuse them for dP^T
-#pragma unroll
-        for (int c = 0; c < NC; ++c) tmem_ld_x32(tDP + 32 * c, d[c]);
+        uint32_t (&d)[CW] = s;                // the S^T registers are dead: reuse them for dP^T
+        ld_cw(tDP, d);
         tmem_ld_wait();
         if (tr_lane) FCSA_TR(2, i, 1);
+        uint32_t ds[CW / 2];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          float dlv[32];
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 dl = lds128f(dla + (32 * c + e) * 4);
-            dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
-          }
-          uint32_t ds[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float2 pa = unpack2<T>(pk[c][e / 2]);
-            const float2 t = __fadd2_rn(make_float2(__uint_as_float(d[c][e]), __uint_as_float(d[c][e + 1])),
-                                        make_float2(dlv[e], dlv[e + 1]));        // dP - delta (delta stored negated)
-            const float2 v = __fmul2_rn(pa, t);
-            ds[e / 2] = pack2<T>(v.x, v.y);
-          }
-          if (c == 0) {
-            mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);        // the dQ product of tile i-1 has left smem dS
-            if (tr_lane) FCSA_TR(2, i, 2);
-          }
-          // packed dS^T over dP^T columns [cq0 + 16c, cq0 + 16c + 16): inside what this warpgroup has loaded
-          tmem_st_x16(tDP + 16 * c, ds);
-          // the same 32 queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
-          const int q0 = cq0 + 32 * c;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            sts128(sDS + (q0 >> 6) * 16384 + sw128_offset(r, ((q0 & 63) >> 3) + q4), ds[4 * q4],
-                   ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]);
+#ifdef FCSA_EXP_NO_DSMATH
+        for (int e = 0; e < CW / 2; ++e) ds[e] = pk[e] ^ d[e] ^ d[e + CW / 2] ^ __float_as_uint(dlv[e]);
+        if (false)
+#endif
+        for (int e = 0; e < CW; e += 2) {
+          const float2 pa = unpack2<T>(pk[e / 2]);
+          const float2 t = __fadd2_rn(make_float2(__uint_as_float(d[e]), __uint_as_float(d[e + 1])),
+                                      make_float2(dlv[e], dlv[e + 1]));        // dP - delta (delta stored negated)
+          const float2 v = __fmul2_rn(pa, t);
+          ds[e / 2] = pack2<T>(v.x, v.y);
         }
+        mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);          // the dQ product of tile i-1 has left smem dS
+        if (tr_lane) FCSA_TR(2, i, 2);
+        // packed dS^T over dP^T columns [cq0, cq0 + CW/2): inside what this warpgroup has loaded
+        st_cw(tDP, ds);
+        // the same CW queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
+#ifndef FCSA_EXP_NO_STS
+#pragma unroll
+        for (int q4 = 0; q4 < CW / 8; ++q4)
+          sts128(sDS + (cq0 >> 6) * 16384 + sw128_offset(r, ((cq0 & 63) >> 3) + q4), ds[4 * q4],
+                 ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]);
+#endif
         tmem_st_wait();
+#ifndef FCSA_EXP_NO_STS
         fence_proxy_async_smem();
+#endif
         tc_fence_before();
         mbar_arrive(BAR(DS_FULL));
         if (tr_lane) FCSA_TR(2, i, 3);
+        // ---- dQ of the previous tile (its MMA was queued behind dK(i-1), dP^T(i): long done)
+        if (i > 0) drain_dq(i - 1);
       }
+      if (NI > 0) drain_dq(NI - 1);
+      if (lane == 0) bulk_wait_group<0>();
+      __syncwarp();
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
+    if (wg < 2) {
     const int w = wg;
     if (NI > 0) {
       mbar_wait(BAR(DKV_FULL), 0);
@@ -693,11 +708,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) tmem_dealloc(tmem, 512);
+  if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------

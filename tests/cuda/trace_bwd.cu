@@ -1,5 +1,7 @@
 // In-kernel timeline of one CTA of the backward kernel at the benchmark shape (4,8,4096,64) causal.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DFCSA_TRACE -o trace_bwd trace_bwd.cu
+// Without -DFCSA_TRACE the same file is a plain timing harness of the main kernel (used for A/B
+// experiments with -DFCSA_EXP_* switches): ... -o time_bwd trace_bwd.cu
 // Test infrastructure only.
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,7 +24,11 @@ __global__ void fillf(float* p, size_t n, float v) {
 }
 
 int main(int argc, char** argv) {
-  const int B = 4, H = 8, N = 4096, D = 64;
+  // usage: [B H Nq Nk causal]   (default: the benchmark shape)
+  const int B = argc > 1 ? atoi(argv[1]) : 4, H = argc > 2 ? atoi(argv[2]) : 8, D = 64;
+  const int Nq = argc > 3 ? atoi(argv[3]) : 4096, Nk = argc > 4 ? atoi(argv[4]) : 4096;
+  const int causal = argc > 5 ? atoi(argv[5]) : 1;
+  const int N = Nq > Nk ? Nq : Nk;                       // allocation size of every tensor
   const size_t n = (size_t)B * H * N * D;
   __nv_bfloat16 *q, *k, *v, *o, *d_o, *dq, *dk, *dv;
   float* inv_l;
@@ -34,11 +40,11 @@ int main(int argc, char** argv) {
   fill<<<(n + 255) / 256, 256>>>(o, n, 4, 1.f);
   fill<<<(n + 255) / 256, 256>>>(d_o, n, 5, 2.f);
   fillf<<<((size_t)B * H * N + 255) / 256, 256>>>(inv_l, (size_t)B * H * N, 1.0f);
-  size_t wsb = fcsa::bwd_workspace_bytes(B, H, H, N, N, D);
+  size_t wsb = fcsa::bwd_workspace_bytes(B, H, H, Nq, Nk, D);
   void* ws;
   CK(cudaMalloc(&ws, wsb));
   fcsa::BwdHostArgs h;
-  h.dtype_bf16 = true; h.B = B; h.H = H; h.kv_heads = H; h.Nq = N; h.Nk = N; h.D = D; h.causal = 1;
+  h.dtype_bf16 = true; h.B = B; h.H = H; h.kv_heads = H; h.Nq = Nq; h.Nk = Nk; h.D = D; h.causal = causal;
   h.scale = 8.f; h.shift = 8.f; h.mask = nullptr; h.mask_sb = 0;
   auto T = [&](void* p) { fcsa_tensor t; t.ptr = p; t.sb = (long long)H * N * D; t.sh = (long long)N * D; t.sn = D; return t; };
   h.q = T(q); h.k = T(k); h.v = T(v); h.o = T(o); h.d_o = T(d_o); h.dq = T(dq); h.dk = T(dk); h.dv = T(dv);
@@ -47,13 +53,24 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   h.ev_start = e0; h.ev_stop = e1;
-  for (int rep = 0; rep < 3; ++rep) {
+#ifdef FCSA_TRACE
+  const int reps = 3;
+#else
+  const int reps = 12;
+#endif
+  float best = 1e9f;
+  for (int rep = 0; rep < reps; ++rep) {
     int r = fcsa::run_backward(h, 0, &launches, &err, &ce);
     if (r) { printf("run_backward failed %d %s\n", r, err ? err : ""); return 1; }
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+#ifdef FCSA_TRACE
     printf("rep %d: main kernel %.1f us\n", rep, ms * 1e3);
+#endif
   }
+  printf("B %d H %d Nq %d Nk %d causal %d: main kernel best of %d: %.1f us\n", B, H, Nq, Nk, causal, reps, best * 1e3);
+#ifdef FCSA_TRACE
   static long long tr[8][48][8];
   CK(cudaMemcpyFromSymbol(tr, g_fcsa_trace, sizeof(tr)));
   long long t0 = tr[1][0][0];
@@ -75,5 +92,6 @@ int main(int argc, char** argv) {
   printf("MMA iteration period (cycles):");
   for (int i = 1; i < 32; ++i) printf(" %lld", tr[1][i][4] - tr[1][i - 1][4]);
   printf("\n");
+#endif
   return 0;
 }
