@@ -203,8 +203,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   enum {
     KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
-    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, DS_FULL, DS_FREE,
-    DQ_FULL, DQ_EMPTY, DKV_FULL, NBARS
+    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, DP_FREE, DS_FULL,
+    DQ_FULL, DKV_FULL, NBARS
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
@@ -247,9 +247,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(BAR(PV_DONE), 1);
     mbar_init(BAR(DP_FULL), 1);
     mbar_init(BAR(DS_FULL), 512);
-    mbar_init(BAR(DS_FREE), 1);
     mbar_init(BAR(DQ_FULL), 1);
-    mbar_init(BAR(DQ_EMPTY), 512);
+    mbar_init(BAR(DP_FREE), 512);
     mbar_init(BAR(DKV_FULL), 2);
     fence_mbar_init();
   }
@@ -335,20 +334,27 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         };
-        // packed dS^T of queries [16kk, 16kk+16): each compute warpgroup keeps its quarter inside its
-        // own QT/4 dP^T columns
+        // packed dS^T of queries [16kk, 16kk+16) lives in the dQ accumulator columns: warpgroup g keeps
+        // its QT/8 packed columns at offset 16g, i.e. inside the 16 accumulator columns it drains itself
         auto ds_col = [](int kk) -> uint32_t {
           constexpr int CW = QT / 4;
           const int w = (16 * kk) / CW;
-          return static_cast<uint32_t>(w * CW + (16 * kk - w * CW) / 2);
+          return static_cast<uint32_t>(w * 16 + (16 * kk - w * CW) / 2);
         };
         mbar_wait(BAR(KV_FULL), 0);
         if (warp == 17) {
+          // chain A: everything that does not depend on dS.  S^T(i+1) as soon as S^T(i) is in
+          // registers, dV(i) when P^T(i) is in X, dP^T(i+1) as soon as dP^T(i) is in registers.
           mbar_wait(BAR(Q_FULL + 0), 0);
           tc_fence_after();
           issue_ST(TM_S, sK, sQ);
           umma_commit(BAR(S_FULL));
           umma_commit(BAR(Q_EMPTY + 0));           // Q(0): this chain is done with it once S^T(0) completes
+          mbar_wait(BAR(DO_FULL + 0), 0);
+          tc_fence_after();
+          issue_ST(TM_DP, sV, sDO);
+          umma_commit(BAR(DP_FULL));
+          umma_commit(BAR(DO_EMPTY + 0));
           for (int i = 0; i < NI; ++i) {
             const int st = i % NST, sn = (i + 1) % NST;
             if (i + 1 < NI) {
@@ -368,28 +374,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                       umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
                       (i > 0 || kk > 0) ? 1u : 0u);
             umma_commit(BAR(PV_DONE));
-            umma_commit(BAR(DO_EMPTY + st));       // dO(i): this chain is done with it
+            umma_commit(BAR(DO_EMPTY + st));       // dO(i): dV is done with it
             FCSA_TR(0, i, 1);
-          }
-          umma_commit(BAR(DKV_FULL));
-        } else {
-          mbar_wait(BAR(DO_FULL + 0), 0);
-          tc_fence_after();
-          issue_ST(TM_DP, sV, sDO);
-          umma_commit(BAR(DP_FULL));
-          umma_commit(BAR(DO_EMPTY + 0));
-          for (int i = 0; i < NI; ++i) {
-            const int st = i % NST, sn = (i + 1) % NST;
-            mbar_wait(BAR(DS_FULL), i & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < QT / 16; ++kk)
-              umma_ts(tmem + TM_DK, tmem + TM_DP + ds_col(kk),
-                      umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(BAR(Q_EMPTY + st));
-            FCSA_TR(0, i, 2);
             if (i + 1 < NI) {
+              mbar_wait(BAR(DP_FREE), i & 1);
               mbar_wait(BAR(DO_FULL + sn), ((i + 1) / NST) & 1);
               tc_fence_after();
               issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
@@ -397,8 +385,22 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               umma_commit(BAR(DO_EMPTY + sn));
               FCSA_TR(0, i, 3);
             }
-            mbar_wait(BAR(DQ_EMPTY), (i & 1) ^ 1);
+          }
+          umma_commit(BAR(DKV_FULL));
+        } else {
+          // chain B: the consumers of dS(i).  dK reads it from TMEM (the dQ accumulator columns),
+          // then dQ(i) overwrites those columns - same issuing thread, in-order pipe.
+          for (int i = 0; i < NI; ++i) {
+            const int st = i % NST;
+            mbar_wait(BAR(DS_FULL), i & 1);
             tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < QT / 16; ++kk)
+              umma_ts(tmem + TM_DK, tmem + TM_DQ + ds_col(kk),
+                      umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(BAR(Q_EMPTY + st));
+            FCSA_TR(0, i, 2);
 #pragma unroll
 #ifdef FCSA_EXP_NO_DQMMA
             if (false)
@@ -410,7 +412,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               else umma_ss(tmem + TM_DQ, d_k, d_ds, idesc_dq, kk > 0 ? 1u : 0u);
             }
             umma_commit(BAR(DQ_FULL));
-            umma_commit(BAR(DS_FREE));
             FCSA_TR(0, i, 4);
           }
           umma_commit(BAR(DKV_FULL));
@@ -439,7 +440,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tS = lane_base + TM_S + cq0;
     const uint32_t tDP = lane_base + TM_DP + cq0;
     const uint32_t tX = lane_base + TM_X + cq0 / 2;
-    const uint32_t tDQ = lane_base + TM_DQ + 16 * wg;
+    const uint32_t tDQ = lane_base + TM_DQ + 16 * wg;       // 16 dQ accumulator columns drained by this warpgroup
+    const uint32_t tDS = tDQ;                                // ... which also hold its packed dS^T (CW/2 columns)
     const uint32_t my_stage = sDQ + wq * 8192 + wg * 2048;     // 2 KB of dQ staging per warp
     const bool tr_lane = (wg == 0 && wq == 0 && lane == 0);
     auto ld_cw = [&](uint32_t addr, uint32_t (&dst)[CW]) {
@@ -450,29 +452,24 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if constexpr (CW == 32) tmem_st_x16(addr, src);
       else tmem_st_x8(addr, src);
     };
-    // dQ of tile j: this warp's 32 rows x 16 accumulator columns
-    auto drain_dq = [&](int j) {
+    // dQ of tile j: this warp's 32 rows x 16 accumulator columns -> registers.  The same (lanes,
+    // columns) receive this thread's packed dS^T of the next tile, so no other thread is involved.
+    uint32_t dqv[16];
+    auto load_dq = [&](int j) {
       mbar_wait(BAR(DQ_FULL), j & 1);
       if (tr_lane) FCSA_TR(3, j, 0);
       tc_fence_after();
-#ifdef FCSA_EXP_NO_DRAIN
-      mbar_arrive(BAR(DQ_EMPTY));
-      return;
-#endif
-      uint32_t q[16];
-      tmem_ld_x16(tDQ, q);
+      tmem_ld_x16(tDQ, dqv);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(BAR(DQ_EMPTY));
       // the previous bulk reduce must have finished reading the staging buffer
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        sts128(my_stage + c * 512 + lane * 16, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
-#ifndef FCSA_EXP_SKIP_DRAIN_FENCE
-      fence_proxy_async_smem();
-#endif
+        sts128(my_stage + c * 512 + lane * 16, dqv[4 * c], dqv[4 * c + 1], dqv[4 * c + 2], dqv[4 * c + 3]);
+    };
+    // after a fence.proxy.async: staged dQ of tile j -> global accumulator (TMA reduce-add, 2 KB)
+    auto reduce_dq = [&](int j) {
       __syncwarp();
 #ifndef FCSA_EXP_SKIP_REDUCE
       if (lane == 0) {
@@ -518,7 +515,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float c3v[CW];
 #pragma unroll
         for (int e = 0; e < CW; e += 4) {
+#ifdef FCSA_EXP_NO_LDS
+          const float4 k0 = make_float4(a.c1, a.scale, a.c1, a.scale);
+#else
           const float4 k0 = lds128f(c3a + e * 4);
+#endif
           c3v[e] = k0.x; c3v[e + 1] = k0.y; c3v[e + 2] = k0.z; c3v[e + 3] = k0.w;
         }
         tmem_ld_wait();
@@ -563,7 +564,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float dlv[CW];
 #pragma unroll
         for (int e = 0; e < CW; e += 4) {
+#ifdef FCSA_EXP_NO_LDS
+          const float4 dl = make_float4(a.c1, a.scale, a.c1, a.scale);
+#else
           const float4 dl = lds128f(dla + e * 4);
+#endif
           dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
         }
         mbar_wait(BAR(DP_FULL), i & 1);
@@ -572,6 +577,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t (&d)[CW] = s;                // the S^T registers are dead: reuse them for dP^T
         ld_cw(tDP, d);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(BAR(DP_FREE));                        // dP^T(i+1) may be produced now
         if (tr_lane) FCSA_TR(2, i, 1);
         uint32_t ds[CW / 2];
 #pragma unroll
@@ -586,10 +593,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const float2 v = __fmul2_rn(pa, t);
           ds[e / 2] = pack2<T>(v.x, v.y);
         }
-        mbar_wait(BAR(DS_FREE), (i & 1) ^ 1);          // the dQ product of tile i-1 has left smem dS
+        // ---- dQ(i-1) out of its accumulator columns (its MMA sits right behind dK(i-1): long done;
+        // it has also released the shared-memory dS^T), then dS^T(i) into them
+        if (i > 0) load_dq(i - 1);
         if (tr_lane) FCSA_TR(2, i, 2);
-        // packed dS^T over dP^T columns [cq0, cq0 + CW/2): inside what this warpgroup has loaded
-        st_cw(tDP, ds);
+        st_cw(tDS, ds);
         // the same CW queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
 #ifndef FCSA_EXP_NO_STS
 #pragma unroll
@@ -598,16 +606,17 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                  ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]);
 #endif
         tmem_st_wait();
-#ifndef FCSA_EXP_NO_STS
-        fence_proxy_async_smem();
-#endif
+        fence_proxy_async_smem();             // covers the dS^T tile and the staged dQ(i-1)
         tc_fence_before();
         mbar_arrive(BAR(DS_FULL));
         if (tr_lane) FCSA_TR(2, i, 3);
-        // ---- dQ of the previous tile (its MMA was queued behind dK(i-1), dP^T(i): long done)
-        if (i > 0) drain_dq(i - 1);
+        if (i > 0) reduce_dq(i - 1);
       }
-      if (NI > 0) drain_dq(NI - 1);
+      if (NI > 0) {
+        load_dq(NI - 1);
+        fence_proxy_async_smem();
+        reduce_dq(NI - 1);
+      }
       if (lane == 0) bulk_wait_group<0>();
       __syncwarp();
     }
@@ -733,15 +742,11 @@ struct DqFinishArgs {
 // (dq_hat - q_hat <q_hat, dq_hat>_group) * rnorm_group on the 8 features one thread owns; the
 // `tpr` threads of a row are consecutive lanes, groups are aligned sub-blocks of them.
 template <typename T>
-__device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishArgs& a, bool ok, int b, int h,
-                                                  int row, int c8) {
+__device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishArgs& a, bool ok, uint4 raw, int b,
+                                                  int h, int row, int c8) {
   if (a.q_rnorm == nullptr) return;            // uniform across the grid
   float y[8];
   {
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (ok)
-      raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh +
-                                            (long long)row * a.q_sn + c8 * 8);
     const float2 u0 = unpack2<T>(raw.x), u1 = unpack2<T>(raw.y), u2 = unpack2<T>(raw.z), u3 = unpack2<T>(raw.w);
     y[0] = u0.x; y[1] = u0.y; y[2] = u1.x; y[3] = u1.y; y[4] = u2.x; y[5] = u2.y; y[6] = u3.x; y[7] = u3.y;
   }
@@ -757,48 +762,68 @@ __device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishA
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = (g[i] - y[i] * dot) * rn;
   } else {
-    for (int g0 = 0; g0 < 8; g0 += gs) {
-      float dot = 0.f;
-      for (int i = 0; i < gs; ++i) dot += y[g0 + i] * g[g0 + i];
-      const float rn = ok ? a.q_rnorm[rbase + (c8 * 8 + g0) / gs] : 0.f;
-      for (int i = 0; i < gs; ++i) g[g0 + i] = (g[g0 + i] - y[g0 + i] * dot) * rn;
+    float pr[8], dot[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pr[i] = y[i] * g[i];
+    subgroup_sums8(pr, gs, dot);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float rn = ok ? a.q_rnorm[rbase + (c8 * 8 + i) / gs] : 0.f;
+      g[i] = (g[i] - y[i] * dot[i]) * rn;
     }
   }
 }
 
 // D = 64: accumulator tile = [4 warps][16 feature-chunks][32 rows][4 features].
-// One thread = 8 consecutive features of one row.
+// One block = one query tile of 128 rows; one thread = 8 consecutive features of FOUR rows (one in
+// each warp-quarter of the tile), all twelve 16-byte loads issued before the first use.
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs a) {
-  // grid = (blocks of 32 rows, batch*heads); 8 threads per row
+  // grid = (query tiles, batch*heads); 8 threads per row
   pdl_launch_dependents();
   pdl_wait();
   const int bh = blockIdx.y;
   const int b = bh / a.H, h = bh - b * a.H;
   const int c8 = threadIdx.x & 7;
-  const int row = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const bool ok = row < a.Nq;
-  const int qt = row >> 7, r = row & 127, wq = r >> 5, rl = r & 31;
-  const float* tile = a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048;
-  float g[8];
-  {
-    float4 lo = make_float4(0, 0, 0, 0), hi = lo;
-    if (ok) {
-      lo = *reinterpret_cast<const float4*>(tile + (2 * c8) * 128 + rl * 4);
-      hi = *reinterpret_cast<const float4*>(tile + (2 * c8 + 1) * 128 + rl * 4);
-    }
-    g[0] = lo.x * a.scale; g[1] = lo.y * a.scale; g[2] = lo.z * a.scale; g[3] = lo.w * a.scale;
-    g[4] = hi.x * a.scale; g[5] = hi.y * a.scale; g[6] = hi.z * a.scale; g[7] = hi.w * a.scale;
+  const int rl = threadIdx.x >> 3;
+  const int qt = blockIdx.x;
+  const float* tile = a.dq_acc + ((long long)bh * a.nqt + qt) * 8192 + rl * 4;
+  float4 lo[4], hi[4];
+  uint4 qraw[4];
+  bool ok[4];
+  int row[4];
+  const bool l2 = a.q_rnorm != nullptr;          // uniform across the grid
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    row[w] = qt * 128 + w * 32 + rl;
+    ok[w] = row[w] < a.Nq;
+    lo[w] = hi[w] = make_float4(0, 0, 0, 0);
+    qraw[w] = make_uint4(0, 0, 0, 0);
   }
-  finish_l2norm_bwd<T>(g, a, ok, b, h, ok ? row : 0, c8);
-  if (ok) {
-    uint4 o4;
-    o4.x = pack2<T>(g[0], g[1]);
-    o4.y = pack2<T>(g[2], g[3]);
-    o4.z = pack2<T>(g[4], g[5]);
-    o4.w = pack2<T>(g[6], g[7]);
-    T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
-    *reinterpret_cast<uint4*>(dst) = o4;
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+    if (ok[w]) {
+      lo[w] = *reinterpret_cast<const float4*>(tile + w * 2048 + (2 * c8) * 128);
+      hi[w] = *reinterpret_cast<const float4*>(tile + w * 2048 + (2 * c8 + 1) * 128);
+      if (l2)
+        qraw[w] = ldg_stream128(reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh +
+                                (long long)row[w] * a.q_sn + c8 * 8);
+    }
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    float g[8];
+    g[0] = lo[w].x * a.scale; g[1] = lo[w].y * a.scale; g[2] = lo[w].z * a.scale; g[3] = lo[w].w * a.scale;
+    g[4] = hi[w].x * a.scale; g[5] = hi[w].y * a.scale; g[6] = hi[w].z * a.scale; g[7] = hi[w].w * a.scale;
+    finish_l2norm_bwd<T>(g, a, ok[w], qraw[w], b, h, ok[w] ? row[w] : 0, c8);
+    if (ok[w]) {
+      uint4 o4;
+      o4.x = pack2<T>(g[0], g[1]);
+      o4.y = pack2<T>(g[2], g[3]);
+      o4.z = pack2<T>(g[4], g[5]);
+      o4.w = pack2<T>(g[6], g[7]);
+      T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row[w] * a.sn + c8 * 8;
+      *reinterpret_cast<uint4*>(dst) = o4;
+    }
   }
 }
 
@@ -832,7 +857,11 @@ __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArg
     float g[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = s[i] * a.scale;
-    finish_l2norm_bwd<T>(g, a, ok, b, h, ok ? row : 0, c8);
+    uint4 qraw = make_uint4(0, 0, 0, 0);
+    if (ok && a.q_rnorm != nullptr)
+      qraw = ldg_stream128(reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh + (long long)row * a.q_sn +
+                           c8 * 8);
+    finish_l2norm_bwd<T>(g, a, ok, qraw, b, h, ok ? row : 0, c8);
     if (ok) {
       uint4 o4;
       o4.x = pack2<T>(g[0], g[1]);
@@ -971,7 +1000,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
     fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
     if (D == 64) {
-      dim3 grid((unsigned)((h.Nq + 31) / 32), (unsigned)(h.B * h.H));
+      dim3 grid((unsigned)w.nqt, (unsigned)(h.B * h.H));
       e = launch_pdl(bwd_dq_finish64_kernel<T>, grid, dim3(256), 0, stream, fa);
     } else {
       e = launch_pdl(bwd_dq_finish128_kernel<T>, dim3((unsigned)((long long)h.B * h.H * w.nqt)), dim3(256), 0, stream, fa);

@@ -22,6 +22,17 @@
 
 namespace {
 
+// SM count of the current device (persistent helper kernels size their grid from it)
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 thread_local char g_err[512] = "";
 cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 std::atomic<long long> g_launches{0};
@@ -273,12 +284,24 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
     if (a.B * a.H > max_bh) max_bh = a.B * a.H;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int rows_per_block = 2 * (256 / (p->head_dim / 8));
-  dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), (unsigned)max_bh, 2);
-  if (max_bh > 65535) return fail(FCSA_ERR_INVALID, "batch*heads > 65535 not supported by the l2norm launch");
-  cudaError_t e = (p->dtype == FCSA_BF16)
-                      ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, pa)
-                      : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half>, grid, dim3(256), 0, s, pa);
+  constexpr int U = 4;                                       // rows per thread per work item
+  const int rows_per_item = U * (256 / (p->head_dim / 8));
+  long long items = 0;
+  for (int t = 0; t < 2; ++t)
+    items += (long long)pa.t[t].B * pa.t[t].H * ((pa.t[t].N + rows_per_item - 1) / rows_per_item);
+  const long long persistent = (long long)sm_count() * 4;    // resident CTAs: 4 x 256 threads per SM
+  dim3 grid((unsigned)(items < persistent ? (items > 0 ? items : 1) : persistent));
+  cudaError_t e;
+  const bool bf = p->dtype == FCSA_BF16;
+  if (p->head_dim == 64)
+    e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 8, U>, grid, dim3(256), 0, s, pa)
+           : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 8, U>, grid, dim3(256), 0, s, pa);
+  else if (p->head_dim == 128)
+    e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 16, U>, grid, dim3(256), 0, s, pa)
+           : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 16, U>, grid, dim3(256), 0, s, pa);
+  else
+    e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 0, U>, grid, dim3(256), 0, s, pa)
+           : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 0, U>, grid, dim3(256), 0, s, pa);
   if (e != cudaSuccess) return cuda_fail(e, "l2norm (q, k) launch");
   g_launches.fetch_add(1);
   return fcsa_forward(p, &n->q_hat, &n->k_hat, v, o, inv_l, stream);

@@ -27,6 +27,19 @@ __device__ __forceinline__ float group_reduce(float v, int tpg) {
   return v;
 }
 
+// Groups narrower than the 8 features one thread owns (group size gs = 1, 2 or 4): for every
+// feature, the sum of v over the aligned gs-wide block it belongs to.  Written with compile-time
+// register indices only - a `for (i < gs)` loop over the arrays would push them to local memory.
+__device__ __forceinline__ void subgroup_sums8(const float (&v)[8], int gs, float (&out)[8]) {
+  float p2[8], p4[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p2[i] = v[i] + v[i ^ 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p4[i] = p2[i] + p2[i ^ 2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = gs == 1 ? v[i] : (gs == 2 ? p2[i] : p4[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
   const int tpr = a.D >> 3;                       // threads per row (8 features each)
@@ -61,14 +74,14 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
     if (ok && a.rnorm && (tr % tpg) == 0) a.rnorm[row * a.G + tr / tpg] = r;
   } else {
     // several groups inside one thread's 8 features (gs = 1, 2 or 4)
+    float sq[8], ss[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) rn[i] = 0.f;
-    for (int g0 = 0; g0 < 8; g0 += gs) {
-      float ss = 0.f;
-      for (int i = 0; i < gs; ++i) ss += f[g0 + i] * f[g0 + i];
-      const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-      for (int i = 0; i < gs; ++i) rn[g0 + i] = r;
-      if (ok && a.rnorm) a.rnorm[row * a.G + (tr * 8 + g0) / gs] = r;
+    for (int i = 0; i < 8; ++i) sq[i] = f[i] * f[i];
+    subgroup_sums8(sq, gs, ss);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      rn[i] = 1.0f / fmaxf(sqrtf(ss[i]), 1e-12f);
+      if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = rn[i];
     }
   }
   if (ok) {
@@ -88,71 +101,111 @@ struct L2PairArgs {
   L2Args t[2];
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
-  // grid = (row blocks, batch*heads, tensor): no per-thread integer division on the address path
+// TPR = threads per row (D / 8) when known at compile time (8 or 16), 0 = read it from the
+// arguments; U = rows per thread per work item.  Persistent: a fixed grid (a few CTAs per SM)
+// strides over the work items (tensor, batch*head, block of U * 256/TPR rows), and the U 16-byte
+// loads of the NEXT item are issued before the current item is reduced and stored, so every SM
+// always has loads in flight (an HBM-bound pass needs ~40 KB in flight per SM to reach the copy
+// rate; short-lived CTAs spend their life ramping up).
+template <typename T, int TPR, int U>
+__global__ void __launch_bounds__(256, 4) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
   pdl_launch_dependents();
   pdl_wait();
-  const L2Args& a = pa.t[blockIdx.z];
-  const int bh = blockIdx.y;
-  if (bh >= a.B * a.H) return;                    // k may have fewer heads than q (block-uniform exit)
-  const int b = bh / a.H, h = bh - b * a.H;
-  const int tpr = a.D >> 3;
-  const int rows_per_block = 256 / tpr;
+  const int tpr = TPR ? TPR : (pa.t[0].D >> 3);
+  const int rows_per_item = U * (256 / tpr);
   const int tr = threadIdx.x % tpr;
-  const int gs = a.D / a.G;
-  const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 8;
-  T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 8;
-  int nn[2];
-  bool ok[2];
-  uint4 raw[2];
+  const int r_in = threadIdx.x / tpr;
+  const int nb0 = (pa.t[0].N + rows_per_item - 1) / rows_per_item;
+  const int nb1 = (pa.t[1].N + rows_per_item - 1) / rows_per_item;
+  const long long cnt0 = (long long)pa.t[0].B * pa.t[0].H * nb0;
+  const long long total = cnt0 + (long long)pa.t[1].B * pa.t[1].H * nb1;
+
+  struct Item { int t, bh, row0; };
+  auto decode = [&](long long w) {
+    Item it;
+    it.t = w >= cnt0;
+    const long long v = it.t ? w - cnt0 : w;
+    const int nb = it.t ? nb1 : nb0;
+    it.bh = (int)(v / nb);
+    it.row0 = (int)(v - (long long)it.bh * nb) * rows_per_item;
+    return it;
+  };
+  auto load = [&](const Item& it, uint4 (&raw)[U]) {
+    const L2Args& a = pa.t[it.t];
+    const int b = it.bh / a.H, h = it.bh - b * a.H;
+    const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 8;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    nn[u] = (blockIdx.x * 2 + u) * rows_per_block + threadIdx.x / tpr;
-    ok[u] = nn[u] < a.N;
-    raw[u] = make_uint4(0, 0, 0, 0);
-  }
-#pragma unroll
-  for (int u = 0; u < 2; ++u)
-    if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(xbase + (long long)nn[u] * a.x_sn);
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const long long row = (long long)bh * a.N + nn[u];
-    float f[8];
-    {
-      float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
-      f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y; f[4] = t2.x; f[5] = t2.y; f[6] = t3.x; f[7] = t3.y;
+    for (int u = 0; u < U; ++u) {
+      const int n = it.row0 + u * (256 / tpr) + r_in;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (n < a.N) raw[u] = ldg_stream128(xbase + (long long)n * a.x_sn);
     }
-    float rn[8];
-    if (gs >= 8) {
-      float ss = 0.f;
+  };
+
+  long long w = blockIdx.x;
+  if (w >= total) return;
+  Item cur = decode(w);
+  uint4 raw[U];
+  load(cur, raw);
+  while (true) {
+    const long long wn = w + gridDim.x;
+    const bool more = wn < total;
+    Item nxt = cur;
+    uint4 raw_n[U];
+    if (more) {
+      nxt = decode(wn);
+      load(nxt, raw_n);
+    }
+    const L2Args& a = pa.t[cur.t];
+    const int b = cur.bh / a.H, h = cur.bh - b * a.H;
+    const int gs = a.D / a.G;
+    T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-      const int tpg = gs >> 3;
-      ss = group_reduce(ss, tpg);
-      const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rn[i] = r;
-      if (ok[u] && a.rnorm && (tr % tpg) == 0) a.rnorm[row * a.G + tr / tpg] = r;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rn[i] = 0.f;
-      for (int g0 = 0; g0 < 8; g0 += gs) {
+    for (int u = 0; u < U; ++u) {
+      const int n = cur.row0 + u * (256 / tpr) + r_in;
+      const bool ok = n < a.N;
+      const long long row = (long long)cur.bh * a.N + n;
+      float f[8];
+      {
+        float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
+        f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y; f[4] = t2.x; f[5] = t2.y; f[6] = t3.x; f[7] = t3.y;
+      }
+      float rn[8];
+      if (gs >= 8) {
         float ss = 0.f;
-        for (int i = 0; i < gs; ++i) ss += f[g0 + i] * f[g0 + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+        const int tpg = gs >> 3;
+        ss = group_reduce(ss, tpg);
         const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-        for (int i = 0; i < gs; ++i) rn[g0 + i] = r;
-        if (ok[u] && a.rnorm) a.rnorm[row * a.G + (tr * 8 + g0) / gs] = r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rn[i] = r;
+        if (ok && a.rnorm && (tr & (tpg - 1)) == 0) a.rnorm[row * a.G + tr / tpg] = r;
+      } else {
+        float sq[8], ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sq[i] = f[i] * f[i];
+        subgroup_sums8(sq, gs, ss);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rn[i] = 1.0f / fmaxf(sqrtf(ss[i]), 1e-12f);
+          if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = rn[i];
+        }
+      }
+      if (ok) {
+        uint4 wv;
+        wv.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
+        wv.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
+        wv.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
+        wv.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
+        *reinterpret_cast<uint4*>(ybase + (long long)n * a.y_sn) = wv;
       }
     }
-    if (ok[u]) {
-      uint4 w;
-      w.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
-      w.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
-      w.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
-      w.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
-      *reinterpret_cast<uint4*>(ybase + (long long)nn[u] * a.y_sn) = w;
-    }
+    if (!more) break;
+    w = wn;
+    cur = nxt;
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = raw_n[u];
   }
 }
 
@@ -195,11 +248,14 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const L2Args a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[i] = (dy[i] - y[i] * dot) * r;
   } else {
-    for (int g0 = 0; g0 < 8; g0 += gs) {
-      float dot = 0.f;
-      for (int i = 0; i < gs; ++i) dot += y[g0 + i] * dy[g0 + i];
-      const float r = ok ? a.rnorm[row * a.G + (tr * 8 + g0) / gs] : 0.f;
-      for (int i = 0; i < gs; ++i) out[g0 + i] = (dy[g0 + i] - y[g0 + i] * dot) * r;
+    float pr[8], dot[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pr[i] = y[i] * dy[i];
+    subgroup_sums8(pr, gs, dot);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r = ok ? a.rnorm[row * a.G + (tr * 8 + i) / gs] : 0.f;
+      out[i] = (dy[i] - y[i] * dot[i]) * r;
     }
   }
   if (ok) {

@@ -47,9 +47,8 @@ int main() {
     a.x = t ? k : q; a.y = t ? kn : qn; a.rnorm = t ? rk : rq;
   }
   {
-    const int rows_per_block = 2 * (256 / (D / 8));
-    dim3 grid((N + rows_per_block - 1) / rows_per_block, B * H, 2);
-    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16><<<grid, 256>>>(pa); }, 4.0 * n * 2);
+    dim3 grid(148 * 4);
+    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 4><<<grid, 256>>>(pa); }, 4.0 * n * 2);
   }
   // prep
   {
@@ -65,7 +64,7 @@ int main() {
     fcsa::DqFinishArgs f; f.B = B; f.H = H; f.Nq = N; f.D = D; f.nqt = w.nqt; f.scale = 8.f;
     f.dq_acc = (float*)((char*)ws + w.dq_off); f.dq = dq; f.sb = sb; f.sh = sh; f.sn = sn;
     f.q_hat = qn; f.q_sb = sb; f.q_sh = sh; f.q_sn = sn; f.q_rnorm = rq; f.G = G;
-    dim3 grid((N + 31) / 32, B * H);
+    dim3 grid(w.nqt, B * H);
     time_it("bwd_dq_finish64 (+l2 bwd)", [&] { fcsa::bwd_dq_finish64_kernel<bf16><<<grid, 256>>>(f); }, n * 4.0 + 2.0 * n * 2);
     f.q_rnorm = nullptr;
     time_it("bwd_dq_finish64 (plain)", [&] { fcsa::bwd_dq_finish64_kernel<bf16><<<grid, 256>>>(f); }, n * 4.0 + n * 2.0);
