@@ -62,7 +62,7 @@ struct BwdCfg {
   static constexpr int kThreads = 640;                  // 16 compute warps + 4 service warps
   // TMEM columns
   static constexpr uint32_t TM_S = 0, TM_DP = QT, TM_DV = 2 * QT, TM_DK = 2 * QT + D, TM_DQ = 2 * QT + 2 * D,
-                            TM_X = 2 * QT + 2 * D + 64;   // QT/2 columns of packed P^T, then dS^T
+                            TM_X = 2 * QT + 2 * D + 64;   // D = 64: K and V as TMEM A operands (2 x 32 packed columns)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -187,6 +187,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr int NST = Cfg::NST;
   constexpr uint32_t TM_S = Cfg::TM_S, TM_DP = Cfg::TM_DP, TM_DV = Cfg::TM_DV, TM_DK = Cfg::TM_DK,
                      TM_DQ = Cfg::TM_DQ, TM_X = Cfg::TM_X;
+  constexpr bool KV_IN_TMEM = (D == 64);   // the X columns hold K (32 packed columns) and V (32): D = 64 only
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -203,7 +204,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   enum {
     KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
-    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, DP_FREE, DS_FULL,
+    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, KV_TMEM, DS_FULL,
     DQ_FULL, DKV_FULL, NBARS
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
@@ -248,7 +249,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(BAR(DP_FULL), 1);
     mbar_init(BAR(DS_FULL), 512);
     mbar_init(BAR(DQ_FULL), 1);
-    mbar_init(BAR(DP_FREE), 512);
+    mbar_init(BAR(KV_TMEM), 256);
     mbar_init(BAR(DKV_FULL), 2);
     fence_mbar_init();
   }
@@ -341,18 +342,47 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const int w = (16 * kk) / CW;
           return static_cast<uint32_t>(w * 16 + (16 * kk - w * CW) / 2);
         };
+        // P^T(i) (A operand of dV) is written, packed, over the dP^T columns its producer has consumed:
+        // warpgroup g keeps its QT/8 packed columns at the start of its own QT/4 dP^T columns
+        auto p_col = [](int kk) -> uint32_t {
+          constexpr int CW = QT / 4;
+          const int w = (16 * kk) / CW;
+          return static_cast<uint32_t>(w * CW + (16 * kk - w * CW) / 2);
+        };
+        // D = 64: K and V also sit in TMEM (the X columns, written once per CTA by the compute warps),
+        // so S^T and dP^T read only their B operand from shared memory
+        auto issue_ST_ts = [&](uint32_t d_col, uint32_t a_col, uint32_t b_smem) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            umma_ts(tmem + d_col, tmem + a_col + k * 8,
+                    umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
+        };
+        auto issue_S = [&](uint32_t q_smem) {
+          if constexpr (KV_IN_TMEM) issue_ST_ts(TM_S, TM_X, q_smem);
+          else issue_ST(TM_S, sK, q_smem);
+        };
+        auto issue_dP = [&](uint32_t do_smem) {
+          if constexpr (KV_IN_TMEM) issue_ST_ts(TM_DP, TM_X + 32, do_smem);
+          else issue_ST(TM_DP, sV, do_smem);
+        };
         mbar_wait(BAR(KV_FULL), 0);
         if (warp == 17) {
           // chain A: everything that does not depend on dS.  S^T(i+1) as soon as S^T(i) is in
-          // registers, dV(i) when P^T(i) is in X, dP^T(i+1) as soon as dP^T(i) is in registers.
+          // registers; dV(i) when P^T(i) is in place; dP^T(i+1) right behind dV(i) (it overwrites
+          // P^T(i): same issuing thread, in-order pipe).
+          if constexpr (KV_IN_TMEM) {
+            mbar_wait(BAR(KV_TMEM), 0);
+            tc_fence_after();
+          }
           mbar_wait(BAR(Q_FULL + 0), 0);
           tc_fence_after();
-          issue_ST(TM_S, sK, sQ);
+          issue_S(sQ);
           umma_commit(BAR(S_FULL));
           umma_commit(BAR(Q_EMPTY + 0));           // Q(0): this chain is done with it once S^T(0) completes
           mbar_wait(BAR(DO_FULL + 0), 0);
           tc_fence_after();
-          issue_ST(TM_DP, sV, sDO);
+          issue_dP(sDO);
           umma_commit(BAR(DP_FULL));
           umma_commit(BAR(DO_EMPTY + 0));
           for (int i = 0; i < NI; ++i) {
@@ -361,7 +391,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               mbar_wait(BAR(S_FREE), i & 1);
               mbar_wait(BAR(Q_FULL + sn), ((i + 1) / NST) & 1);
               tc_fence_after();
-              issue_ST(TM_S, sK, sQ + sn * Cfg::kQ);
+              issue_S(sQ + sn * Cfg::kQ);
               umma_commit(BAR(S_FULL));
               umma_commit(BAR(Q_EMPTY + sn));
               FCSA_TR(0, i, 0);
@@ -370,17 +400,16 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < QT / 16; ++kk)
-              umma_ts(tmem + TM_DV, tmem + TM_X + kk * 8,
+              umma_ts(tmem + TM_DV, tmem + TM_DP + p_col(kk),
                       umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
                       (i > 0 || kk > 0) ? 1u : 0u);
             umma_commit(BAR(PV_DONE));
             umma_commit(BAR(DO_EMPTY + st));       // dO(i): dV is done with it
             FCSA_TR(0, i, 1);
             if (i + 1 < NI) {
-              mbar_wait(BAR(DP_FREE), i & 1);
               mbar_wait(BAR(DO_FULL + sn), ((i + 1) / NST) & 1);
               tc_fence_after();
-              issue_ST(TM_DP, sV, sDO + sn * Cfg::kQ);
+              issue_dP(sDO + sn * Cfg::kQ);
               umma_commit(BAR(DP_FULL));
               umma_commit(BAR(DO_EMPTY + sn));
               FCSA_TR(0, i, 3);
@@ -439,7 +468,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int cq0 = wg * CW;
     const uint32_t tS = lane_base + TM_S + cq0;
     const uint32_t tDP = lane_base + TM_DP + cq0;
-    const uint32_t tX = lane_base + TM_X + cq0 / 2;
+    const uint32_t tP = lane_base + TM_DP + cq0;             // packed P^T goes over the dP^T columns this thread has read
     const uint32_t tDQ = lane_base + TM_DQ + 16 * wg;       // 16 dQ accumulator columns drained by this warpgroup
     const uint32_t tDS = tDQ;                                // ... which also hold its packed dS^T (CW/2 columns)
     const uint32_t my_stage = sDQ + wq * 8192 + wg * 2048;     // 2 KB of dQ staging per warp
@@ -480,6 +509,27 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #endif
       if (tr_lane) FCSA_TR(3, j, 1);
     };
+    if constexpr (KV_IN_TMEM) {
+      // K (warpgroup 0) and V (warpgroup 1) rows -> TMEM as A operands: 64 features = 32 packed columns
+      if (wg < 2 && NI > 0) {
+        mbar_wait(BAR(KV_FULL), 0);
+        const uint32_t src = wg == 0 ? sK : sV;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t kv[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 v4 = lds128f(src + sw128_offset(r, 4 * hf + c));
+            kv[4 * c] = __float_as_uint(v4.x); kv[4 * c + 1] = __float_as_uint(v4.y);
+            kv[4 * c + 2] = __float_as_uint(v4.z); kv[4 * c + 3] = __float_as_uint(v4.w);
+          }
+          tmem_st_x16(lane_base + TM_X + 32 * wg + 16 * hf, kv);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(BAR(KV_TMEM));
+      }
+    }
     {
       const float c1 = a.c1;
       bool key_ok = key_g < a.Nk;
@@ -552,15 +602,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (need_mask) exp_tile(std::true_type{});
         else exp_tile(std::false_type{});
         if (tr_lane) FCSA_TR(1, i, 3);
-        // X still holds P^T(i-1) until dV(i-1) has read it
-        if (i > 0) mbar_wait(BAR(PV_DONE), (i - 1) & 1);
-        st_cw(tX, pk);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(BAR(P_FULL));
-        if (tr_lane) FCSA_TR(1, i, 4);
-
-        // ---- dS stage
+        // ---- dP^T(i) into registers first: P^T(i) is then written over the columns it occupied
+        // (DP_FULL(i) also tells that dV(i-1) has finished reading P^T(i-1): same in-order pipe)
         float dlv[CW];
 #pragma unroll
         for (int e = 0; e < CW; e += 4) {
@@ -577,8 +620,11 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t (&d)[CW] = s;                // the S^T registers are dead: reuse them for dP^T
         ld_cw(tDP, d);
         tmem_ld_wait();
+        st_cw(tP, pk);
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(BAR(DP_FREE));                        // dP^T(i+1) may be produced now
+        mbar_arrive(BAR(P_FULL));
+        if (tr_lane) FCSA_TR(1, i, 4);
         if (tr_lane) FCSA_TR(2, i, 1);
         uint32_t ds[CW / 2];
 #pragma unroll
