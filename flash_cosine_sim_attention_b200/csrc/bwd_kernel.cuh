@@ -57,8 +57,18 @@ struct BwdCfg {
   static constexpr int kOffDS = kOffDO + NST * kQ;
   static constexpr int kOffDQ = kOffDS + kDS;             // fp32 staging 128 x 64 = 32 KB
   static constexpr int kOffStats = kOffDQ + 32768;        // NST stages x 1 KB (2*QT floats used)
-  static constexpr int kOffBar = kOffStats + NST * 1024;
+  // D = 64: the per-query constants reach the accumulators through one extra K = 16 MMA step
+  // ("augmented" contraction) instead of through per-column shared-memory loads:
+  //   ones   : 128 keys x 16, columns 0..2 = 1                      (A operand, 4 KB, once per CTA)
+  //   aug S  : QT queries x 16, columns 0..2 = c3/c1 split in three 16-bit parts   (B operand)
+  //   aug dP : QT queries x 16, columns 0..2 = -delta split in three 16-bit parts  (B operand)
+  static constexpr bool kAug = (D == 64);
+  static constexpr int kSliver = QT * 32;                 // bytes of one QT x 16 sliver
+  static constexpr int kOffOnes = kOffStats + NST * 1024;
+  static constexpr int kOffAug = kOffOnes + (kAug ? 4096 : 0);        // NST stages x {aug S, aug dP}
+  static constexpr int kOffBar = kOffAug + (kAug ? NST * 2 * kSliver : 0);
   static constexpr int kSmem = kOffBar + 256 + 1024;
+  static_assert(kSmem <= 232448, "backward kernel shared memory");
   static constexpr int kThreads = 640;                  // 16 compute warps + 4 service warps
   // TMEM columns
   static constexpr uint32_t TM_S = 0, TM_DP = QT, TM_DV = 2 * QT, TM_DK = 2 * QT + D, TM_DQ = 2 * QT + 2 * D,
@@ -72,9 +82,11 @@ struct BwdCfg {
 //           reduce warps produce it (D = 64: lane = query row, chunk = 4 features;
 //           D = 128: lane = feature, chunk = 4 query rows)
 //   dkv_acc (kv_heads == 1 < heads only): dk [B][Nk][D] then dv [B][Nk][D]
+//   aug   : 16-bit [B*H][nqt*QT][32]  cols 0..2 = c3/c1 in three parts, cols 16..18 = -delta in three
+//           parts, rest 0 (the extra K = 16 step of S^T and dP^T, D = 64); ones: 16-bit [128][16]
 // ------------------------------------------------------------------------------------------
 struct BwdWorkspace {
-  size_t stats_off, dq_off, dkv_off, total;
+  size_t stats_off, dq_off, dkv_off, aug_off, ones_off, total;
   int nqt, QT;
 };
 
@@ -86,10 +98,14 @@ inline BwdWorkspace bwd_workspace_layout(int B, int H, int kv_heads, int Nq, int
   size_t dq = (size_t)B * H * w.nqt * 32768;
   size_t dkv = (kv_heads == 1 && H > 1) ? (size_t)2 * B * Nk * D * 4 : 0;
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  // augmented-contraction operands (16-bit): [B*H][nqt*QT][32] and the 128 x 16 ones tile
+  size_t aug = (size_t)B * H * w.nqt * w.QT * 32 * 2;
   w.stats_off = 0;
   w.dq_off = up(stats);
   w.dkv_off = w.dq_off + up(dq);
-  w.total = w.dkv_off + up(dkv);
+  w.aug_off = w.dkv_off + up(dkv);
+  w.ones_off = w.aug_off + up(aug);
+  w.total = w.ones_off + 4096;
   return w;
 }
 
@@ -108,7 +124,21 @@ struct PrepArgs {
   const float* inv_l;               // (B, H, Nq)
   float* stats;
   float* dq_acc;                    // zeroed here (32 bytes per thread) instead of a separate memset
+  void* aug;                        // 16-bit [B*H][nqt*QT][32] (see workspace layout) or nullptr
+  void* ones;                       // 16-bit [128][16]
+  float inv_c1;                     // 1 / (scale * log2e)
 };
+
+// x = p0 + p1 + p2 with each part representable in T (16 bit): 24 bits of x survive
+template <typename T>
+__device__ __forceinline__ void split3(float x, uint32_t& w01, uint32_t& w2) {
+  const float2 r0 = unpack2<T>(pack2<T>(x, 0.f));
+  const float e1 = x - r0.x;
+  const float2 r1 = unpack2<T>(pack2<T>(e1, 0.f));
+  const float e2 = e1 - r1.x;
+  w01 = pack2<T>(r0.x, r1.x);
+  w2 = pack2<T>(e2, 0.f);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
@@ -152,6 +182,22 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
     }
     st[r] = c3;
     st[a.QT + r] = -dl;      // stored negated: the dS stage computes P * (dP + (-delta)) with packed adds
+    if (a.aug) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.aug) + ((long long)bh * padded + row) * 64);
+      uint4 s0 = make_uint4(0, 0, 0, 0), d0 = s0;
+      if (valid) {
+        split3<T>(c3 * a.inv_c1, s0.x, s0.y);
+        split3<T>(-dl, d0.x, d0.y);
+      }
+      dst[0] = s0; dst[1] = make_uint4(0, 0, 0, 0);
+      dst[2] = d0; dst[3] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (a.aug && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 128) {
+    uint4* dst = reinterpret_cast<uint4*>(a.ones) + threadIdx.x * 2;
+    const uint32_t one2 = pack2<T>(1.f, 1.f), one1 = pack2<T>(1.f, 0.f);
+    dst[0] = make_uint4(one2, one1, 0, 0);
+    dst[1] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -178,6 +224,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(640, 1)
 fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_aug, const __grid_constant__ CUtensorMap tm_ones,
                 const BwdArgs a) {
   static_assert(D == 64 || D == 128, "head dim 64 or 128");
   using Cfg = BwdCfg<D>;
@@ -187,7 +234,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr int NST = Cfg::NST;
   constexpr uint32_t TM_S = Cfg::TM_S, TM_DP = Cfg::TM_DP, TM_DV = Cfg::TM_DV, TM_DK = Cfg::TM_DK,
                      TM_DQ = Cfg::TM_DQ, TM_X = Cfg::TM_X;
-  constexpr bool KV_IN_TMEM = (D == 64);   // the X columns hold K (32 packed columns) and V (32): D = 64 only
+  constexpr bool KV_IN_TMEM = (D == 64);
+  constexpr bool AUG = Cfg::kAug;          // per-query constants enter through an extra K = 16 MMA step   // the X columns hold K (32 packed columns) and V (32): D = 64 only
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -199,6 +247,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t sDS = smem_u32(smem + Cfg::kOffDS);
   const uint32_t sDQ = smem_u32(smem + Cfg::kOffDQ);
   const uint32_t sStats = smem_u32(smem + Cfg::kOffStats);
+  const uint32_t sOnes = smem_u32(smem + Cfg::kOffOnes);
+  const uint32_t sAug = smem_u32(smem + Cfg::kOffAug);     // stage st: S sliver, then dP sliver
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -288,29 +338,35 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == 16) {
       // =============================== TMA producer ===============================
       if (NI > 0 && elect_one()) {
-        mbar_expect_tx(BAR(KV_FULL), 2 * Cfg::kKV);
+        mbar_expect_tx(BAR(KV_FULL), 2 * Cfg::kKV + (AUG ? 4096 : 0));
 #pragma unroll
         for (int ch = 0; ch < KCH; ++ch) {
           tma_load_4d(sK + ch * 16384, &tm_k, BAR(KV_FULL), ch * 64, key0, hk, b);
           tma_load_4d(sV + ch * 16384, &tm_v, BAR(KV_FULL), ch * 64, key0, hk, b);
         }
+        if constexpr (AUG) tma_load_4d(sOnes, &tm_ones, BAR(KV_FULL), 0, 0, 0, 0);
         for (int i = 0; i < NI; ++i) {
           const int st = i % NST, qt = i_lo + i;
           const uint32_t par = ((i / NST) & 1) ^ 1;
           mbar_wait(BAR(Q_EMPTY + st), par);
           FCSA_TR(4, i, 0);
-          mbar_expect_tx(BAR(Q_FULL + st), Cfg::kQ + 8 * QT);
+          mbar_expect_tx(BAR(Q_FULL + st), Cfg::kQ + (AUG ? Cfg::kSliver : 8 * QT));
 #pragma unroll
           for (int ch = 0; ch < KCH; ++ch)
             tma_load_4d(sQ + st * Cfg::kQ + ch * QCHUNK, &tm_q, BAR(Q_FULL + st), ch * 64, qt * QT, h, b);
-          bulk_load_1d(sStats + st * 1024,
-                       a.stats + ((long long)bh * a.nqt + qt) * 2 * QT, 8 * QT, BAR(Q_FULL + st));
+          if constexpr (AUG)
+            tma_load_4d(sAug + st * 2 * Cfg::kSliver, &tm_aug, BAR(Q_FULL + st), 0, qt * QT, bh, 0);
+          else
+            bulk_load_1d(sStats + st * 1024,
+                         a.stats + ((long long)bh * a.nqt + qt) * 2 * QT, 8 * QT, BAR(Q_FULL + st));
           mbar_wait(BAR(DO_EMPTY + st), par);
           FCSA_TR(4, i, 1);
-          mbar_expect_tx(BAR(DO_FULL + st), Cfg::kQ);
+          mbar_expect_tx(BAR(DO_FULL + st), Cfg::kQ + (AUG ? Cfg::kSliver : 0));
 #pragma unroll
           for (int ch = 0; ch < KCH; ++ch)
             tma_load_4d(sDO + st * Cfg::kQ + ch * QCHUNK, &tm_do, BAR(DO_FULL + st), ch * 64, qt * QT, h, b);
+          if constexpr (AUG)
+            tma_load_4d(sAug + st * 2 * Cfg::kSliver + Cfg::kSliver, &tm_aug, BAR(DO_FULL + st), 16, qt * QT, bh, 0);
         }
       }
     } else if (warp == 17 || warp == 18) {
@@ -358,13 +414,21 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         };
-        auto issue_S = [&](uint32_t q_smem) {
+        // st = ring stage of the Q / dO tile (and of its sliver)
+        auto issue_S = [&](int st) {
+          const uint32_t q_smem = sQ + st * Cfg::kQ;
           if constexpr (KV_IN_TMEM) issue_ST_ts(TM_S, TM_X, q_smem);
           else issue_ST(TM_S, sK, q_smem);
+          if constexpr (AUG)      // S^T += ones * (c3/c1)^T : the exponent offset of every query column
+            umma_ss(tmem + TM_S, umma_desc_sw32(sOnes), umma_desc_sw32(sAug + st * 2 * Cfg::kSliver), idesc_s, 1u);
         };
-        auto issue_dP = [&](uint32_t do_smem) {
+        auto issue_dP = [&](int st) {
+          const uint32_t do_smem = sDO + st * Cfg::kQ;
           if constexpr (KV_IN_TMEM) issue_ST_ts(TM_DP, TM_X + 32, do_smem);
           else issue_ST(TM_DP, sV, do_smem);
+          if constexpr (AUG)      // dP^T += ones * (-delta)^T
+            umma_ss(tmem + TM_DP, umma_desc_sw32(sOnes),
+                    umma_desc_sw32(sAug + st * 2 * Cfg::kSliver + Cfg::kSliver), idesc_s, 1u);
         };
         mbar_wait(BAR(KV_FULL), 0);
         if (warp == 17) {
@@ -377,12 +441,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           mbar_wait(BAR(Q_FULL + 0), 0);
           tc_fence_after();
-          issue_S(sQ);
+          issue_S(0);
           umma_commit(BAR(S_FULL));
           umma_commit(BAR(Q_EMPTY + 0));           // Q(0): this chain is done with it once S^T(0) completes
           mbar_wait(BAR(DO_FULL + 0), 0);
           tc_fence_after();
-          issue_dP(sDO);
+          issue_dP(0);
           umma_commit(BAR(DP_FULL));
           umma_commit(BAR(DO_EMPTY + 0));
           for (int i = 0; i < NI; ++i) {
@@ -391,7 +455,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               mbar_wait(BAR(S_FREE), i & 1);
               mbar_wait(BAR(Q_FULL + sn), ((i + 1) / NST) & 1);
               tc_fence_after();
-              issue_S(sQ + sn * Cfg::kQ);
+              issue_S(sn);
               umma_commit(BAR(S_FULL));
               umma_commit(BAR(Q_EMPTY + sn));
               FCSA_TR(0, i, 0);
@@ -409,7 +473,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (i + 1 < NI) {
               mbar_wait(BAR(DO_FULL + sn), ((i + 1) / NST) & 1);
               tc_fence_after();
-              issue_dP(sDO + sn * Cfg::kQ);
+              issue_dP(sn);
               umma_commit(BAR(DP_FULL));
               umma_commit(BAR(DO_EMPTY + sn));
               FCSA_TR(0, i, 3);
@@ -562,15 +626,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t pk[CW / 2];                 // P^T packed; lives until the dS stage below
         uint32_t s[CW];
         ld_cw(tS, s);
-        float c3v[CW];
+        float c3v[AUG ? 2 : CW];
+        if constexpr (!AUG) {
 #pragma unroll
-        for (int e = 0; e < CW; e += 4) {
-#ifdef FCSA_EXP_NO_LDS
-          const float4 k0 = make_float4(a.c1, a.scale, a.c1, a.scale);
-#else
-          const float4 k0 = lds128f(c3a + e * 4);
-#endif
-          c3v[e] = k0.x; c3v[e + 1] = k0.y; c3v[e + 2] = k0.z; c3v[e + 3] = k0.w;
+          for (int e = 0; e < CW; e += 4) {
+            const float4 k0 = lds128f(c3a + e * 4);
+            c3v[e] = k0.x; c3v[e + 1] = k0.y; c3v[e + 2] = k0.z; c3v[e + 3] = k0.w;
+          }
         }
         tmem_ld_wait();
         tc_fence_before();
@@ -580,8 +642,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
           for (int e = 0; e < CW; e += 2) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])),
-                                        make_float2(c1, c1), make_float2(c3v[e], c3v[e + 1]));
+            const float2 sv = make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+            float2 x;
+            if constexpr (AUG) x = __fmul2_rn(sv, make_float2(c1, c1));     // the accumulator already holds s + c3/c1
+            else x = __ffma2_rn(sv, make_float2(c1, c1), make_float2(c3v[AUG ? 0 : e], c3v[AUG ? 1 : e + 1]));
             // some of the pairs on the FMA pipe (cubic minimax exp2), the rest on the MUFU
             const bool poly = FCSA_BWD_POLY_EVERY > 0 && ((e / 2) % (FCSA_BWD_POLY_EVERY > 0 ? FCSA_BWD_POLY_EVERY : 1)) == FCSA_BWD_POLY_EVERY - 1;
 #ifdef FCSA_EXP_NO_EXP
@@ -604,15 +668,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr_lane) FCSA_TR(1, i, 3);
         // ---- dP^T(i) into registers first: P^T(i) is then written over the columns it occupied
         // (DP_FULL(i) also tells that dV(i-1) has finished reading P^T(i-1): same in-order pipe)
-        float dlv[CW];
+        float dlv[AUG ? 2 : CW];
+        if constexpr (!AUG) {
 #pragma unroll
-        for (int e = 0; e < CW; e += 4) {
-#ifdef FCSA_EXP_NO_LDS
-          const float4 dl = make_float4(a.c1, a.scale, a.c1, a.scale);
-#else
-          const float4 dl = lds128f(dla + e * 4);
-#endif
-          dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
+          for (int e = 0; e < CW; e += 4) {
+            const float4 dl = lds128f(dla + e * 4);
+            dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
+          }
         }
         mbar_wait(BAR(DP_FULL), i & 1);
         if (tr_lane) FCSA_TR(2, i, 0);
@@ -628,14 +690,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr_lane) FCSA_TR(2, i, 1);
         uint32_t ds[CW / 2];
 #pragma unroll
-#ifdef FCSA_EXP_NO_DSMATH
-        for (int e = 0; e < CW / 2; ++e) ds[e] = pk[e] ^ d[e] ^ d[e + CW / 2] ^ __float_as_uint(dlv[e]);
-        if (false)
-#endif
         for (int e = 0; e < CW; e += 2) {
           const float2 pa = unpack2<T>(pk[e / 2]);
-          const float2 t = __fadd2_rn(make_float2(__uint_as_float(d[e]), __uint_as_float(d[e + 1])),
-                                      make_float2(dlv[e], dlv[e + 1]));        // dP - delta (delta stored negated)
+          float2 t = make_float2(__uint_as_float(d[e]), __uint_as_float(d[e + 1]));   // AUG: already dP - delta
+          if constexpr (!AUG) t = __fadd2_rn(t, make_float2(dlv[AUG ? 0 : e], dlv[AUG ? 1 : e + 1]));  // delta stored negated
           const float2 v = __fmul2_rn(pa, t);
           ds[e / 2] = pack2<T>(v.x, v.y);
         }
@@ -995,6 +1053,9 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     pa.o = h.o.ptr; pa.o_sb = h.o.sb; pa.o_sh = h.o.sh; pa.o_sn = h.o.sn;
     pa.d_o = h.d_o.ptr; pa.do_sb = h.d_o.sb; pa.do_sh = h.d_o.sh; pa.do_sn = h.d_o.sn;
     pa.inv_l = h.inv_l; pa.stats = stats; pa.dq_acc = dq_acc;
+    pa.aug = Cfg::kAug ? ws + w.aug_off : nullptr;
+    pa.ones = ws + w.ones_off;
+    pa.inv_c1 = 1.0f / (h.scale * log2e);
     const int rows_per_block = 256 / (D / 8);
     const int padded = w.nqt * Cfg::QT;
     dim3 grid((unsigned)((padded + rows_per_block - 1) / rows_per_block), (unsigned)(h.B * h.H));
@@ -1012,6 +1073,19 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
         make_tensor_map_bhnd(&tdo, h.d_o.ptr, h.dtype_bf16, h.B, h.H, h.Nq, D, h.d_o.sb, h.d_o.sh, h.d_o.sn, Cfg::QT)) {
       *err = "cuTensorMapEncodeTiled failed (backward)";
       return FCSA_ERR_INVALID;
+    }
+    // slivers of the augmented contraction: 16 columns x QT rows out of the [B*H][nqt*QT][32] tensor,
+    // and the constant 128 x 16 ones tile (32-byte rows: SWIZZLE_32B).  D = 128 does not use them.
+    CUtensorMap taug = tq, tones = tq;
+    if (Cfg::kAug) {
+      const long long padded = (long long)w.nqt * Cfg::QT;
+      if (make_tensor_map_bhnd(&taug, ws + w.aug_off, h.dtype_bf16, 1, (long long)h.B * h.H, padded, 32,
+                               (long long)h.B * h.H * padded * 32, padded * 32, 32, Cfg::QT, 16, 32) ||
+          make_tensor_map_bhnd(&tones, ws + w.ones_off, h.dtype_bf16, 1, 1, 128, 16, 128 * 16, 128 * 16, 16, 128,
+                               16, 32)) {
+        *err = "cuTensorMapEncodeTiled failed (backward, slivers)";
+        return FCSA_ERR_INVALID;
+      }
     }
     BwdArgs a;
     a.B = h.B; a.H = h.H; a.Nq = h.Nq; a.Nk = h.Nk; a.kv_heads = h.kv_heads; a.causal = h.causal;
@@ -1033,7 +1107,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     }
     const long long grid = (long long)((h.Nk + 127) / 128) * h.B * h.H;
     if (h.ev_start) cudaEventRecord(h.ev_start, stream);
-    e = launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, tdo, a);
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, tdo, taug, tones, a);
     if (h.ev_stop) cudaEventRecord(h.ev_stop, stream);
     if (e != cudaSuccess) { *err = "backward kernel launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;

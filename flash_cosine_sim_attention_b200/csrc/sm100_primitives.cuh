@@ -252,6 +252,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 
+// K-major operand that is exactly ONE K = 16 step wide: what a TMA SWIZZLE_32B box of 16 16-bit
+// elements x R rows leaves in shared memory (row r at byte r*32, XOR-swizzled inside 256-byte atoms).
+// SBO = 256 (next 8 rows); layout type 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 (fp16/bf16 inputs, fp32 accumulate).
 //   [4,6) D format (1 = f32)   [7,10) A format   [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major  [16] B major (0 = K-major, 1 = MN-major)   [17,23) N>>3   [24,29) M>>4

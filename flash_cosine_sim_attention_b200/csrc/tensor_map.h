@@ -32,12 +32,13 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // Tensor map over a 16-bit tensor addressed as [b][h][n][d] with element strides
-// (sb, sh, sn, 1).  The box is 64 features x box_rows rows (one 128-byte swizzle span).
+// (sb, sh, sn, 1).  The box is box_cols features x box_rows rows: 64 features = one 128-byte swizzle
+// span for the operand tiles, 16 features = one 32-byte span (swizzle_bytes = 32) for the K = 16 slivers.
 // A dimension of extent 1 gets a dummy stride (the driver rejects zero strides).
 // Returns 0 on success, else the CUresult.
 inline int make_tensor_map_bhnd(CUtensorMap* tm, const void* base, bool is_bf16, int64_t B,
                                 int64_t H, int64_t N, int64_t D, int64_t sb, int64_t sh, int64_t sn,
-                                int box_rows, int box_cols = 64) {
+                                int box_rows, int box_cols = 64, int swizzle_bytes = 128) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return -1;
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
@@ -51,7 +52,9 @@ inline int make_tensor_map_bhnd(CUtensorMap* tm, const void* base, bool is_bf16,
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                        : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }

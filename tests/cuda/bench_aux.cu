@@ -52,7 +52,7 @@ int main() {
   }
   // prep
   {
-    fcsa::PrepArgs p; p.B = B; p.H = H; p.Nq = N; p.D = D; p.nqt = w.nqt; p.QT = w.QT; p.c2 = 11.5f;
+    fcsa::PrepArgs p; p.aug = nullptr; p.ones = nullptr; p.inv_c1 = 1.f; p.B = B; p.H = H; p.Nq = N; p.D = D; p.nqt = w.nqt; p.QT = w.QT; p.c2 = 11.5f;
     p.o = o; p.o_sb = sb; p.o_sh = sh; p.o_sn = sn; p.d_o = d_o; p.do_sb = sb; p.do_sh = sh; p.do_sn = sn;
     p.inv_l = inv_l; p.stats = (float*)((char*)ws + w.stats_off); p.dq_acc = (float*)((char*)ws + w.dq_off);
     const int rows_per_block = 256 / (D / 8);
