@@ -6,11 +6,15 @@
 // key-padding mask, cu:1198-1212) - completely different machine mapping:
 //
 //   * one CTA owns 256 query rows of one (batch, head): two 128-row tiles that ping-pong
-//   * warp 8   : TMA producer   (Q once, K and V tiles through mbarrier rings)
-//   * warps 9,10: tcgen05 issuers, one per query tile (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with
-//                P_t read from TMEM); warp 11 idles
-//   * warps 0-3: "softmax" warpgroup for tile 0, warps 4-7 for tile 1: thread == query row,
-//                tcgen05.ld S -> exp2(fma) -> row sum in a register -> 16-bit P -> tcgen05.st
+//   * warp 16  : TMA producer   (Q once, K and V tiles through mbarrier rings)
+//   * warps 17,18: tcgen05 issuers, one per query tile (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with
+//                P_t read from TMEM); warp 19 idles
+//   * warps 0-7: "softmax" warps of tile 0, warps 8-15 of tile 1.  Per tile two warpgroups, each on
+//                one half of the 128 key columns (thread == query row x 64 columns):
+//                tcgen05.ld S -> exp2(fma) -> partial row sum in registers -> 16-bit P -> tcgen05.st.
+//                Four warps per scheduler all on the exp stage hide each other's TMEM / MUFU latency;
+//                the two partial row sums of a row meet once, in the epilogue (there is no running
+//                max, so nothing else couples the two halves of a row).
 //   * TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).  Because there is
 //     no row max there is no rescaling of O: the accumulator never leaves TMEM until the epilogue.
 //     D = 64 : P0 [384,448) P1 [448,512) (packed 16-bit pairs) are separate columns, so the
@@ -51,13 +55,14 @@ struct FwdCfg {
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = 2 * kTile;
   static constexpr int kOffV = kOffK + kKS * kTile;
-  static constexpr int kOffBar = kOffV + kVS * kTile;
+  static constexpr int kOffL = kOffV + kVS * kTile;   // partial row sums: 2 tiles x 2 halves x 128 floats
+  static constexpr int kOffBar = kOffL + 2048;
   static constexpr int kSmem = kOffBar + 256 + 1024;  // + alignment slack
-  static constexpr int kThreads = 384;
+  static constexpr int kThreads = 640;                // 16 softmax warps + 4 service warps
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FwdArgs a) {
   using Cfg = FwdCfg<D>;
@@ -111,7 +116,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int NT = max(n_t[0], n_t[1]);
 
   // ---- one-time setup ------------------------------------------------------------------
-  if (warp == 8 && elect_one()) {
+  if (warp == 16 && elect_one()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -126,14 +131,14 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(BAR(S_FULL + t), 1);
-      mbar_init(BAR(P_FULL + t), 128);
+      mbar_init(BAR(P_FULL + t), 256);
       mbar_init(BAR(O_FULL + t), 1);
-      mbar_init(BAR(S_FREE + t), 128);
+      mbar_init(BAR(S_FREE + t), 256);
       mbar_init(BAR(P_FREE + t), 1);
     }
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == 17) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
@@ -143,7 +148,8 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
   pdl_wait();          // q, k (normalised by the previous kernel), v, mask are read from here on
 
-  if (warp == 8) {
+  if (warp >= 16) reg_dealloc<64>();      // 4 x 104 + 64 = 5 x 96: the pool is what the CTA was launched with
+  if (warp == 16) {
     // =============================== TMA producer ===============================
     // (elect_one, not lane == 0: ptxas then keeps descriptors/addresses in uniform registers
     //  instead of wrapping every UTMALDG/UTCHMMA in a divergence "waterfall" loop)
@@ -168,13 +174,13 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_load_4d(sV + vs * TILE + ch * 16384, &tm_v, BAR(V_FULL + vs), ch * 64, j * 128, hk, b);
       }
     }
-  } else if (warp == 9 || warp == 10) {
+  } else if (warp == 17 || warp == 18) {
     // =============================== MMA issuers ================================
-    // One issuing thread per query tile (warp 9: tile 0, warp 10: tile 1).  Each follows only its
+    // One issuing thread per query tile (warp 17: tile 0, warp 18: tile 1).  Each follows only its
     // own softmax warpgroup (S_t(j+1) when S_t(j) is in registers, P_t(j) V_j when P_t(j) is stored),
     // so neither tile ever waits behind the other's barriers; the tensor pipe interleaves the two
     // instruction streams.  K / V ring slots are released by both (barrier count 2).
-    const int t = warp - 9;
+    const int t = warp - 17;
     if (NT > 0 && elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc<T>(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc<T>(128, D, 0, 1);
@@ -237,42 +243,47 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 16) {
     // =============================== softmax warpgroups =========================
-    const int t = warp >> 2;                 // which 128-row tile
+    reg_alloc<104>();
+    const int t = warp >> 3;                 // which 128-row tile
+    const int half = (warp >> 2) & 1;        // which 64 of the 128 key columns of every tile
     const int wq = warp & 3;                 // TMEM lane quarter this warp may touch
     const int r = wq * 32 + lane;            // row inside the tile
     const int row_g = m0 + 128 * t + r;      // global query row
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t tS = lane_base + t * 128;
-    const uint32_t tP = PSEP ? lane_base + 384 + t * 64 : tS + 64;
+    const uint32_t tS = lane_base + t * 128 + 64 * half;
+    const uint32_t tP = (PSEP ? lane_base + 384 + t * 64 : lane_base + t * 128 + 64) + 32 * half;
     const uint32_t tO = lane_base + 256 + t * D;
     const int nt = n_t[t];
     const float c1 = a.c1, nc2 = -a.c2;
     float l = 0.f;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // unmasked tiles accumulate here
 
-    const bool tr_lane = (wq == 0 && lane == 0);
+    const bool tr_lane = (half == 0 && wq == 0 && lane == 0);
     for (int j = 0; j < nt; ++j) {
       if (tr_lane) FCSA_TR(1 + t, j, 0);
       mbar_wait(BAR(S_FULL + t), j & 1);
       if (tr_lane) FCSA_TR(1 + t, j, 1);
       tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
+      uint32_t s0[32], s1[32];
       tmem_ld_x32(tS + 0, s0);
       tmem_ld_x32(tS + 32, s1);
-      tmem_ld_x32(tS + 64, s2);
-      tmem_ld_x32(tS + 96, s3);
       tmem_ld_wait();
       if (tr_lane) FCSA_TR(1 + t, j, 2);
-      if (PSEP) {
-        tc_fence_before();
-        mbar_arrive(BAR(S_FREE + t));                       // S_t may be overwritten by tile j+1 now
-      }
-      // before the first store of P(j): P_t(j-1) V must have finished reading the P columns.  Waited
-      // for as late as possible - after the first chunk of exps - so it never costs anything.
+      tc_fence_before();
+      mbar_arrive(BAR(S_FREE + t));            // PSEP: S_t may be overwritten by tile j+1 now
+      // before the first store of P(j):
+      //   PSEP : P_t(j-1) V must have finished reading the P columns
+      //   !PSEP: P_t overwrites the upper half of S_t - the other warpgroup's columns: it must hold them
+      //          in registers (S_FREE doubles as that rendezvous; the issuer does not wait on it)
+      // Waited for as late as possible - after the first chunk of exps - so it rarely costs anything.
       auto p_cols_free = [&]() {
-        if (PSEP && j > 0) mbar_wait(BAR(P_FREE + t), (j - 1) & 1);
+        if (PSEP) {
+          if (j > 0) mbar_wait(BAR(P_FREE + t), (j - 1) & 1);
+        } else {
+          mbar_wait(BAR(S_FREE + t), j & 1);
+        }
       };
       if (tr_lane) FCSA_TR(1 + t, j, 3);
 
@@ -301,18 +312,16 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         };
         chunk(s0, 0);
         chunk(s1, 1);
-        chunk(s2, 2);
-        chunk(s3, 3);
       } else {
         // visible iff column <= lim (causal / ragged end) and key-mask bit set
         int lim = a.Nk - 1;
         if (a.causal) lim = min(lim, row_g + off);
         lim -= col0;
-        uint32_t kw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        uint32_t kw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
         if (a.has_mask) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int col = col0 + w * 32 + lane;
+          for (int w = 0; w < 2; ++w) {
+            const int col = col0 + (2 * half + w) * 32 + lane;
             const uint8_t mv = (col < a.Nk) ? a.mask[(long long)b * a.mask_sb + col] : uint8_t(0);
             kw[w] = __ballot_sync(0xFFFFFFFFu, mv != 0);
           }
@@ -322,7 +331,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint32_t word = kw[c];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int cc0 = c * 32 + 2 * i, cc1 = cc0 + 1;
+            const int cc0 = (2 * half + c) * 32 + 2 * i, cc1 = cc0 + 1;
             float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c1, nc2));
             float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c1, nc2));
             p0 = (cc0 <= lim && ((word >> (2 * i)) & 1u)) ? p0 : 0.f;
@@ -335,8 +344,6 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         };
         chunk(s0, 0);
         chunk(s1, 1);
-        chunk(s2, 2);
-        chunk(s3, 3);
       }
       if (tr_lane) FCSA_TR(1 + t, j, 4);
       tmem_st_wait();
@@ -346,18 +353,26 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     // ---- epilogue: O * 1/max(l, eps) -> global ----------------------------------------
-    // the clamp only guards rows with no visible key (l == 0, O == 0 -> o = 0; reference: cu:1239 uses
-    // 1e-10, too large here because shift = scale*groups makes legitimately tiny row sums)
+    // The two column halves of a row exchange their partial sums through shared memory, then each
+    // stores half of the D output features.  The clamp only guards rows with no visible key (l == 0,
+    // O == 0 -> o = 0; reference: cu:1239 uses 1e-10, too large here because shift = scale*groups
+    // makes legitimately tiny row sums).
     l += (l2a.x + l2a.y) + (l2b.x + l2b.y);
+    float* lbuf = reinterpret_cast<float*>(smem + Cfg::kOffL) + t * 256;
+    lbuf[half * 128 + r] = l;
+    named_bar_sync(1 + t, 256);
+    l += lbuf[(half ^ 1) * 128 + r];
     const float inv = 1.0f / fmaxf(l, 1e-37f);
     const bool row_ok = row_g < a.Nq;
     T* orow = reinterpret_cast<T*>(a.o) + (long long)b * a.o_sb + (long long)h * a.o_sh +
               (long long)row_g * a.o_sn;
+    constexpr int CPH = D / 64;              // 32-column chunks of O per half
     if (nt > 0) {
       mbar_wait(BAR(O_FULL + t), 0);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int cc = 0; cc < CPH; ++cc) {
+        const int c = half * CPH + cc;
         uint32_t acc[32];
         tmem_ld_x32(tO + c * 32, acc);
         tmem_ld_wait();
@@ -375,16 +390,17 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     } else if (row_ok) {
 #pragma unroll
-      for (int v = 0; v < D / 8; ++v) *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(0, 0, 0, 0);
+      for (int v = 0; v < D / 16; ++v)
+        *reinterpret_cast<uint4*>(orow + half * (D / 2) + v * 8) = make_uint4(0, 0, 0, 0);
     }
-    if (row_ok && a.inv_l != nullptr)
+    if (half == 0 && row_ok && a.inv_l != nullptr)
       a.inv_l[((long long)b * a.H + h) * a.Nq + row_g] = inv;
   }
 
   // ---- teardown ------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 512);
+  if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace fcsa
