@@ -24,6 +24,8 @@
 //              behind P_t(j) V_j in the (in-order) tensor pipe.
 #pragma once
 
+#include <type_traits>
+
 #include "sm100_primitives.cuh"
 
 #ifndef FCSA_POLY_EVERY
@@ -203,7 +205,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         // The two softmax warpgroups share the MUFU pipe: started half a tile apart, one computes at
         // full rate while the other is in its per-tile overhead (TMEM load/store, barriers).
+#ifndef FCSA_FWD_NO_STAGGER
         if (t == 1 && n_t[0] > 0) mbar_wait(BAR(P_FULL + 0), 0);
+#endif
         issue_S(0);
       }
       for (int j = 0; j < NT; ++j) {
@@ -258,7 +262,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int nt = n_t[t];
     const float c1 = a.c1, nc2 = -a.c2;
     float l = 0.f;
-    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // unmasked tiles accumulate here
+    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // two partial row-sum chains
 
     const bool tr_lane = (half == 0 && wq == 0 && lane == 0);
     for (int j = 0; j < nt; ++j) {
@@ -313,37 +317,42 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         chunk(s0, 0);
         chunk(s1, 1);
       } else {
+        // Masked tiles (diagonal, ragged end, key-padding mask): the same packed math plus one select
+        // per element, driven by a per-thread visibility word per 32-column chunk:
         // visible iff column <= lim (causal / ragged end) and key-mask bit set
         int lim = a.Nk - 1;
         if (a.causal) lim = min(lim, row_g + off);
         lim -= col0;
-        uint32_t kw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (a.has_mask) {
+        uint32_t vis[2];
 #pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const int col = col0 + (2 * half + w) * 32 + lane;
+        for (int w = 0; w < 2; ++w) {
+          const int c0 = (2 * half + w) * 32;                       // first column of the chunk, tile-relative
+          uint32_t word = 0xFFFFFFFFu;
+          if (a.has_mask) {
+            const int col = col0 + c0 + lane;
             const uint8_t mv = (col < a.Nk) ? a.mask[(long long)b * a.mask_sb + col] : uint8_t(0);
-            kw[w] = __ballot_sync(0xFFFFFFFFu, mv != 0);
+            word = __ballot_sync(0xFFFFFFFFu, mv != 0);
           }
+          const int nvis = lim - c0 + 1;                            // columns of this chunk at or below lim
+          const uint32_t range = nvis >= 32 ? 0xFFFFFFFFu : (nvis <= 0 ? 0u : ((1u << nvis) - 1u));
+          vis[w] = word & range;
         }
-        auto chunk = [&](const uint32_t(&s)[32], int c) {
+        const float2 c1v = make_float2(c1, c1), c2v = make_float2(nc2, nc2);
+        auto chunk = [&](const uint32_t(&s)[32], int c, uint32_t v) {
           uint32_t pk[16];
-          const uint32_t word = kw[c];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int cc0 = (2 * half + c) * 32 + 2 * i, cc1 = cc0 + 1;
-            float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c1, nc2));
-            float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c1, nc2));
-            p0 = (cc0 <= lim && ((word >> (2 * i)) & 1u)) ? p0 : 0.f;
-            p1 = (cc1 <= lim && ((word >> (2 * i + 1)) & 1u)) ? p1 : 0.f;
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c1v, c2v);
+            const float p0 = ((v >> (2 * i)) & 1u) ? ex2_approx(x.x) : 0.f;
+            const float p1 = ((v >> (2 * i + 1)) & 1u) ? ex2_approx(x.y) : 0.f;
             l += p0 + p1;
             pk[i] = pack2<T>(p0, p1);
           }
           if (c == 0) p_cols_free();
           tmem_st_x16(tP + c * 16, pk);
         };
-        chunk(s0, 0);
-        chunk(s1, 1);
+        chunk(s0, 0, vis[0]);
+        chunk(s1, 1, vis[1]);
       }
       if (tr_lane) FCSA_TR(1 + t, j, 4);
       tmem_st_wait();

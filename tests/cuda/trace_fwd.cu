@@ -17,8 +17,13 @@ __global__ void fill(__nv_bfloat16* p, size_t n, unsigned seed, float amp) {
   p[i] = __float2bfloat16(((x & 0xFFFF) / 65536.0f - 0.5f) * amp);
 }
 
-int main() {
-  const int B = 4, H = 8, N = 4096, D = 64;
+int main(int argc, char** argv) {
+  // usage: [B H Nq Nk causal]  (default: the benchmark shape).  Without -DFCSA_TRACE this is a plain
+  // timing harness (A/B experiments): ... -o time_fwd trace_fwd.cu
+  const int B = argc > 1 ? atoi(argv[1]) : 4, H = argc > 2 ? atoi(argv[2]) : 8, D = 64;
+  const int Nq = argc > 3 ? atoi(argv[3]) : 4096, Nk = argc > 4 ? atoi(argv[4]) : 4096;
+  const int causal = argc > 5 ? atoi(argv[5]) : 1;
+  const int N = Nq > Nk ? Nq : Nk;
   const size_t n = (size_t)B * H * N * D;
   __nv_bfloat16 *q, *k, *v, *o;
   float* inv_l;
@@ -29,11 +34,11 @@ int main() {
   fill<<<(n + 255) / 256, 256>>>(v, n, 3, 2.f);
   CUtensorMap tq, tk, tv;
   long long sb = (long long)H * N * D, sh = (long long)N * D, sn = D;
-  if (fcsa::make_tensor_map_bhnd(&tq, q, true, B, H, N, D, sb, sh, sn, 128) ||
-      fcsa::make_tensor_map_bhnd(&tk, k, true, B, H, N, D, sb, sh, sn, 128) ||
-      fcsa::make_tensor_map_bhnd(&tv, v, true, B, H, N, D, sb, sh, sn, 128)) { printf("tmap fail\n"); return 1; }
+  if (fcsa::make_tensor_map_bhnd(&tq, q, true, B, H, Nq, D, sb, sh, sn, 128) ||
+      fcsa::make_tensor_map_bhnd(&tk, k, true, B, H, Nk, D, sb, sh, sn, 128) ||
+      fcsa::make_tensor_map_bhnd(&tv, v, true, B, H, Nk, D, sb, sh, sn, 128)) { printf("tmap fail\n"); return 1; }
   fcsa::FwdArgs a;
-  a.B = B; a.H = H; a.Nq = N; a.Nk = N; a.causal = 1; a.has_mask = 0; a.kv_heads = H; a.n_qblk = N / 256;
+  a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.causal = causal; a.has_mask = 0; a.kv_heads = H; a.n_qblk = (Nq + 255) / 256;
   a.c1 = 8.f * 1.44269504f; a.c2 = a.c1; a.mask = nullptr; a.mask_sb = 0;
   a.o = o; a.o_sb = sb; a.o_sh = sh; a.o_sn = sn; a.inv_l = inv_l;
   using Cfg = fcsa::FwdCfg<D>;
@@ -41,14 +46,22 @@ int main() {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int rep = 0; rep < 3; ++rep) {
+#ifdef FCSA_TRACE
+  const int reps = 3;
+#else
+  const int reps = 12;
+#endif
+  float best = 1e9f;
+  for (int rep = 0; rep < reps; ++rep) {
     CK(cudaEventRecord(e0));
     kern<<<a.n_qblk * B * H, Cfg::kThreads, Cfg::kSmem>>>(tq, tk, tv, a);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-    printf("rep %d: fwd kernel %.1f us\n", rep, ms * 1e3);
+    if (ms < best) best = ms;
   }
+  printf("B %d H %d Nq %d Nk %d causal %d: fwd kernel best of %d: %.1f us\n", B, H, Nq, Nk, causal, reps, best * 1e3);
+#ifdef FCSA_TRACE
   static long long tr[8][48][8];
   CK(cudaMemcpyFromSymbol(tr, g_fcsa_trace, sizeof(tr)));
   long long t0 = tr[1][0][0];
@@ -65,5 +78,6 @@ int main() {
   printf("SM0 period:");
   for (int i = 1; i < 31; ++i) printf(" %lld", tr[1][i][1] - tr[1][i - 1][1]);
   printf("\n");
+#endif
   return 0;
 }
