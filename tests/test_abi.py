@@ -83,6 +83,7 @@ def test_workspace_size_formula(lib):
     n = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
     stats = 4 * 8 * 32 * 256 * 4
     dq = 4 * 8 * 4096 * 64 * 4
-    assert n == stats + dq
+    aug = 4 * 8 * 4096 * 32 * 2 + 4096      # 16-bit slivers of the augmented contraction + the ones tile
+    assert n == stats + dq + aug
     p.kv_heads = 1
-    assert lib.fcsa_backward_workspace_bytes(_abi.ref(p)) == stats + dq + 2 * 4 * 4096 * 64 * 4
+    assert lib.fcsa_backward_workspace_bytes(_abi.ref(p)) == stats + dq + aug + 2 * 4 * 4096 * 64 * 4
