@@ -9,7 +9,8 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract; in short:
   value        whole-job TFLOP/s, inputs resident in HBM, timed with CUDA events per step
                (an L2 flush runs between steps, outside the events)
   e2e          the same metric through the public API starting from pinned HOST buffers:
-               H2D of q,k,v,d_out and D2H of o,dq,dk,dv inside the timed region
+               H2D of q,k,v,d_out and D2H of o,dq,dk,dv of every step inside the timed region
+               (upload / compute / download on three streams, double-buffered across steps)
   roofline     the dominant kernel (the tcgen05 backward kernel), timed live with events recorded
                around exactly that launch, against the measured bf16 peak (MEASURED_PEAKS.json)
   cpu_baseline the oracle's torch-f32 port of the reference's naive path on the host cores
@@ -205,20 +206,52 @@ def main():
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
 
     # ---- end to end from pinned host buffers ---------------------------------------------------
-    houts = [torch.empty(B, H, N, D, dtype=dt).pin_memory() for _ in range(4)]
-    def e2e_step():
-        qq, kk, vv, dd = (t.to(dev, non_blocking=True) for t in host)
-        qq.requires_grad_(), kk.requires_grad_(), vv.requires_grad_()
-        outs = step(qq, kk, vv, dd)
-        for dst, src in zip(houts, outs):
-            dst.copy_(src.detach(), non_blocking=True)
-    for _ in range(2):
-        e2e_step()
+    # Every step copies its four inputs host->device and its four results device->host; the copies
+    # are inside the timed region.  Three streams (upload, compute, download) and two sets of device
+    # buffers: the upload of step i+1 and the download of step i-1 run under the compute of step i,
+    # the way an input pipeline feeds a training loop.  The compute is the public API call.
+    houts = [[torch.empty(B, H, N, D, dtype=dt).pin_memory() for _ in range(4)] for _ in range(2)]
+    dins = [[torch.empty(B, H, N, D, dtype=dt, device=dev) for _ in range(4)] for _ in range(2)]
+    for bufs in dins:
+        for t in bufs[:3]:
+            t.requires_grad_()
+    s_up, s_cmp, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_up = [torch.cuda.Event() for _ in range(2)]      # inputs of buffer set b are on the device
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]     # results of buffer set b are computed (inputs consumed)
+    ev_dn = [torch.cuda.Event() for _ in range(2)]      # results of buffer set b are on the host
+
+    def e2e_run(n):
+        keep = [None, None]
+        for i in range(n):
+            bsel = i & 1
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(ev_cmp[bsel])               # step i-2 has consumed this buffer set
+                with torch.no_grad():
+                    for dst, src in zip(dins[bsel], host):
+                        dst.copy_(src, non_blocking=True)
+                ev_up[bsel].record(s_up)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_up[bsel])
+                outs = step(*dins[bsel])
+                ev_cmp[bsel].record(s_cmp)
+            with torch.cuda.stream(s_dn):
+                s_dn.wait_event(ev_cmp[bsel])
+                s_dn.wait_event(ev_dn[bsel])                # host buffers of step i-2 are written
+                for dst, src in zip(houts[bsel], outs):
+                    src.record_stream(s_dn)
+                    dst.copy_(src.detach(), non_blocking=True)
+                ev_dn[bsel].record(s_dn)
+            keep[bsel] = outs
+        for st in (s_up, s_cmp, s_dn):
+            torch.cuda.current_stream().wait_stream(st)
+
+    e2e_run(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        e2e_step()
+    for st in (s_up, s_cmp, s_dn):
+        st.wait_stream(torch.cuda.current_stream())
+    e2e_run(K)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
