@@ -329,10 +329,12 @@ class _FusedCosineSimAttention(Function):
     """One autograd node for l2norm(q), l2norm(k) -> attention, all in CUDA kernels."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mask, scale, causal, groups, l2norm_qk):
+    def forward(ctx, q, k, v, mask, scale, causal, groups, l2norm_qk, shift_groups=0):
         sh = _Shapes(q, k, v)
         mask_u8 = _prep_mask(mask, sh)
-        shift = _choose_shift(q.dtype, scale, groups, l2norm_qk)
+        # shift_groups > 0: q, k arrive already normalised over that many groups (padded head dims)
+        shift = (_choose_shift(q.dtype, scale, shift_groups, True) if shift_groups > 0
+                 else _choose_shift(q.dtype, scale, groups, l2norm_qk))
         needs_grad = any(ctx.needs_input_grad[:3])
         if l2norm_qk:
             o, inv_l, qn, kn, rq, rk = _attn_forward_fused(q, k, v, mask_u8, scale, shift, causal, groups,
@@ -353,7 +355,7 @@ class _FusedCosineSimAttention(Function):
             dq, dk, dv = _attn_backward_fused(do, o, inv_l, qn, kn, v, rq, rk, mask_u8, scale, shift, causal, groups)
         else:
             dq, dk, dv = _attn_backward(do, o, inv_l, qn, kn, v, mask_u8, scale, shift, causal)
-        return dq, dk, dv, None, None, None, None, None
+        return dq, dk, dv, None, None, None, None, None, None
 
 
 class _L2Norm(Function):
@@ -452,8 +454,22 @@ def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
         raise RuntimeError(
             "flash_cosine_sim_attention: CUDA tensors required - this build has no CPU path "
             "(use plain_cosine_sim_attention on CPU tensors)")
+    D = q.shape[-1]
+    if (q.dtype in _KERNEL_DTYPES and k.dtype == q.dtype and v.dtype == q.dtype and not exists(attn_bias)
+            and D not in _KERNEL_HEAD_DIMS and D < 128 and D % 8 == 0 and D % groups == 0):
+        # Head dims the kernels are not instantiated for (the reference's 32 and 96): zero-pad the
+        # features to 64 / 128 and run the same tcgen05 kernels.  Zero features change neither q.k nor
+        # the norms (the l2norm runs first, on the real features), the padded output columns are
+        # zero and sliced off; autograd takes care of the slices.  Costs two pad copies per tensor.
+        Dp = 64 if D < 64 else 128
+        if l2norm_qk:
+            q, k = _l2norm_torch(q, groups), _l2norm_torch(k, groups)
+        pad = lambda t: torch.nn.functional.pad(t, (0, Dp - D))
+        o = _FusedCosineSimAttention.apply(pad(q), pad(k), pad(v), mask, float(scale), bool(causal), 1, False,
+                                           int(groups) if l2norm_qk else 0)
+        return o[..., :D]
     if not _kernel_supported(q, k, v, attn_bias):
-        # float32 inputs, head dims other than 64/128 and attn_bias have no sm_100a kernel yet:
+        # float32 inputs, head dims above 128 / not a multiple of 8, and attn_bias have no sm_100a kernel yet:
         # they run the un-fused formulation on the same GPU (correct, slower), never silently wrong.
         why = ("attn_bias" if exists(attn_bias) else
                f"dtype {q.dtype}" if q.dtype not in _KERNEL_DTYPES else f"head_dim {q.shape[-1]}")

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_OUT = {torch.bfloat16: 1e-2, torch.float16: 2e-3}
 TOL_GRAD = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
-BWD_HEAD_DIMS = (64, 128)
+BWD_HEAD_DIMS = (32, 64, 96, 128)   # 32 and 96 run the 64 / 128 kernels on zero-padded features
 ROUND = {torch.bfloat16: "bf16", torch.float16: "f16"}   # the op stores normalised q, k in the input dtype
 
 
@@ -92,6 +92,16 @@ def test_reference_grid(fcsa, causal, mask, seq_len, dim_head, dtype, single_hea
     kvs = (batch, seq_len, dim_head) if single_head_kv else (batch, heads, seq_len, dim_head)
     check(fcsa, (batch, heads, seq_len, dim_head), kvs, dtype, seed=seq_len + dim_head,
           mask_p=0.5 if mask else None, causal=causal)
+
+
+# ---- the remaining head dims of the reference grid (tests/test.py:33): zero-padded onto the same kernels
+@pytest.mark.parametrize("causal,mask", [(True, False), (False, True)])
+@pytest.mark.parametrize("dim_head,groups", [(32, 1), (96, 1), (32, 2), (96, 3)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_padded_head_dims(fcsa, causal, mask, dim_head, groups, dtype):
+    check(fcsa, (2, 4, 127, dim_head), (2, 4, 127, dim_head), dtype, seed=dim_head + groups,
+          mask_p=0.5 if mask else None, causal=causal, groups=groups,
+          scale=8 if groups == 1 or dtype == torch.bfloat16 else 4)
 
 
 # ---- committed golden vectors produced by the unmodified reference --------------------------------
