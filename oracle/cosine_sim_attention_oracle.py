@@ -104,7 +104,9 @@ def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=Fals
     similarity (what the reference's l2norm_tensors does for 16-bit inputs, py:64); gradients flow
     through the rounding unchanged, as autograd does through a dtype cast.
 
-    Returns o, or (o, dq, dk, dv) when d_out is given.  Shapes follow the inputs."""
+    Returns o, or (o, dq, dk, dv) when d_out is given - plus d_bias (shape of attn_bias: dS summed
+    over the batch unless the bias has a batch dimension, cu:1574-1576) when a bias is given too.
+    Shapes follow the inputs."""
     assert not (causal and mask is not None), "mask should not be supplied if causality is needed"
     q0, k0, v0 = (np.asarray(t, dtype=F64) for t in (q, k, v))
     q4, k4, v4, merged, single_head_kv = _canon(q0, k0, v0)
@@ -127,6 +129,7 @@ def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=Fals
         dqn = np.zeros_like(qn)
         dkn = np.zeros_like(kn)
         dv4 = np.zeros_like(v4)
+        dbias = None if attn_bias is None else np.zeros(np.asarray(attn_bias).shape, dtype=F64)
     for b in range(B):
         vis = _visibility(b, Nq, Nk, mask, causal)
         any_vis = vis.any(-1)
@@ -155,6 +158,8 @@ def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=Fals
                     ds[~any_vis] = 0.0      # the logits of such rows are constants (-max)
                 dqn[b, h] = scale * (ds @ kn[b, hk])
                 dkn[b, hk] += scale * (ds.T @ qn[b, h])
+                if dbias is not None:
+                    dbias[b if attn_bias_batch_dim else h] += ds
     out = o[:, 0] if merged else o
     if not want_grad:
         return out
@@ -167,6 +172,8 @@ def attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=Fals
         dq = dq[:, 0]
     if single_head_kv:
         dk, dv4 = dk[:, 0], dv4[:, 0]
+    if dbias is not None:
+        return out, dq, dk, dv4, dbias
     return out, dq, dk, dv4
 
 

@@ -36,6 +36,10 @@ CASES = {
     "merged_bh_groups4_scale1": dict(q=(6, 33, 64), kv=(6, 33, 64), kw=dict(groups=4, scale=1)),
     "d128_causal_scale10": dict(q=(1, 2, 64, 128), kv=(1, 2, 64, 128), kw=dict(causal=True, scale=10)),
     "no_l2norm": dict(q=(1, 2, 48, 64), kv=(1, 2, 48, 64), kw=dict(l2norm_qk=False, scale=1), small=True),
+    # attn_bias (reference tests/test.py:58-61): per head, and with a batch dimension on merged batch-heads
+    "bias_heads_causal": dict(q=(2, 3, 80, 64), kv=(2, 3, 80, 64), kw=dict(causal=True), bias=(3, 80, 80)),
+    "bias_heads_mask_cross": dict(q=(2, 2, 40, 64), kv=(2, 2, 72, 64), kw=dict(), mask=True, bias=(2, 40, 72)),
+    "bias_batch_dim_merged": dict(q=(4, 56, 64), kv=(4, 56, 64), kw=dict(attn_bias_batch_dim=True), bias=(4, 56, 56)),
 }
 
 
@@ -63,14 +67,23 @@ def main():
         if c.get("mask"):
             mask = torch.rand((c["q"][0], c["kv"][-2]), generator=g) > 0.3
             mask[:, 0] = True   # no fully-masked rows (plain and fused differ there by design)
-        o = ref.plain_cosine_sim_attention(q, k, v, mask=mask, **c["kw"])
+        bias = None
+        if c.get("bias"):
+            bias = r16(torch.randn(c["bias"], generator=g, dtype=torch.float64)).requires_grad_()
+        kw_ref = dict(c["kw"], attn_bias=bias) if bias is not None else c["kw"]
+        o = ref.plain_cosine_sim_attention(q, k, v, mask=mask, **kw_ref)
         do = r16(torch.randn(o.shape, generator=g, dtype=torch.float64))
         (o * do).sum().backward()
 
         args = dict(mask=None if mask is None else mask.numpy(), d_out=do.numpy(), **c["kw"])
-        oo, dq, dk, dv = oracle.attention(q.detach().numpy(), k.detach().numpy(), v.detach().numpy(), **args)
+        if bias is not None:
+            args["attn_bias"] = bias.detach().numpy()
+        res = oracle.attention(q.detach().numpy(), k.detach().numpy(), v.detach().numpy(), **args)
+        oo, dq, dk, dv = res[:4]
         errs = [np.abs(oo - o.detach().numpy()).max(), np.abs(dq - q.grad.numpy()).max(),
                 np.abs(dk - k.grad.numpy()).max(), np.abs(dv - v.grad.numpy()).max()]
+        if bias is not None:
+            errs.append(np.abs(res[4] - bias.grad.numpy()).max())
         assert max(errs) < 1e-9, (name, errs)
         np.savez_compressed(
             os.path.join(out_dir, name + ".npz"),
@@ -79,8 +92,10 @@ def main():
             mask=np.zeros(0, dtype=bool) if mask is None else mask.numpy(),
             o=o.detach().numpy(), dq=q.grad.numpy(), dk=k.grad.numpy(), dv=v.grad.numpy(),
             kwargs=np.array(repr(c["kw"])),
+            **({} if bias is None else dict(attn_bias=bias.detach().numpy().astype(np.float32),
+                                            d_bias=bias.grad.numpy())),
         )
-        print(f"{name}: oracle vs reference max err fwd/dq/dk/dv = " + " ".join(f"{e:.2e}" for e in errs))
+        print(f"{name}: oracle vs reference max err fwd/dq/dk/dv(/dbias) = " + " ".join(f"{e:.2e}" for e in errs))
 
 
 if __name__ == "__main__":

@@ -117,6 +117,10 @@ def test_reference_golden_vectors(fcsa, path):
     grads = z["q"].shape[-1] in BWD_HEAD_DIMS
     q, k, v = (torch.from_numpy(z[n]).to(dt).cuda().requires_grad_(grads) for n in ("q", "k", "v"))
     assert np.array_equal(q.detach().float().cpu().numpy(), z["q"])
+    bias = None
+    if "attn_bias" in z.files:
+        bias = torch.from_numpy(z["attn_bias"]).to(dt).cuda().requires_grad_(grads)
+        kw = dict(kw, attn_bias=bias)
     o = fcsa.flash_cosine_sim_attention(q, k, v, mask=mask, **kw)
     want = {n: z[n] for n in ("o", "dq", "dk", "dv")}
     if kw.get("causal") and z["q"].shape[-2] > z["k"].shape[-2]:
@@ -130,6 +134,9 @@ def test_reference_golden_vectors(fcsa, path):
         o.backward(torch.from_numpy(z["d_out"]).to(dt).cuda())
         for name, t in (("dq", q), ("dk", k), ("dv", v)):
             assert rel_err(t.grad, want[name]) <= TOL_GRAD[dt], name
+        if bias is not None:
+            assert bias.grad is not None and bias.grad.shape == bias.shape
+            assert rel_err(bias.grad, z["d_bias"]) <= TOL_GRAD[dt], "d_bias"
 
 
 # ---- features the reference never tested (SURVEY.md par. 4) ----------------------------------------

@@ -20,14 +20,17 @@ def load_case(path):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 8
+    assert len(GOLDEN) >= 11
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_oracle_matches_reference_golden(path):
     z, kw, mask = load_case(path)
-    o, dq, dk, dv = oracle.attention(z["q"], z["k"], z["v"], mask=mask, d_out=z["d_out"], **kw)
-    for name, got in (("o", o), ("dq", dq), ("dk", dk), ("dv", dv)):
+    bias = z["attn_bias"] if "attn_bias" in z.files else None
+    res = oracle.attention(z["q"], z["k"], z["v"], mask=mask, attn_bias=bias, d_out=z["d_out"], **kw)
+    names = ("o", "dq", "dk", "dv") + (("d_bias",) if bias is not None else ())
+    assert len(res) == len(names)
+    for name, got in zip(names, res):
         assert got.shape == z[name].shape
         assert np.abs(got - z[name]).max() < 1e-9, name
 
