@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = (
     "fcsa_set_kernel_events",
     "fcsa_forward_fused",
     "fcsa_backward_fused",
+    "fcsa_forward_bias",
+    "fcsa_backward_bias",
 )
 
 
@@ -61,6 +63,10 @@ class FcsaProblem(Structure):
 class FcsaL2Norm(Structure):
     _fields_ = [("groups", c_int32), ("q_hat", FcsaTensor), ("k_hat", FcsaTensor), ("q_rnorm", c_void_p),
                 ("k_rnorm", c_void_p)]
+
+
+class FcsaBias(Structure):
+    _fields_ = [("ptr", c_void_p), ("sb", c_int64), ("sh", c_int64), ("sn", c_int64)]
 
 
 class FcsaError(RuntimeError):
@@ -106,6 +112,12 @@ def load():
     lib.fcsa_forward_fused.argtypes = [PP, PT, PT, PT, PN, PT, c_void_p, c_void_p]
     lib.fcsa_backward_fused.restype = c_int32
     lib.fcsa_backward_fused.argtypes = [PP, PN, PT, PT, PT, c_void_p, PT, PT, PT, c_void_p, c_size_t, c_void_p]
+    PB = POINTER(FcsaBias)
+    lib.fcsa_forward_bias.restype = c_int32
+    lib.fcsa_forward_bias.argtypes = [PP, PT, PT, PT, PB, PT, c_void_p, c_void_p]
+    lib.fcsa_backward_bias.restype = c_int32
+    lib.fcsa_backward_bias.argtypes = [PP, PT, PT, PT, PT, PT, c_void_p, PB, c_void_p, c_int64, c_int64,
+                                       PT, PT, PT, c_void_p, c_size_t, c_void_p]
     lib.fcsa_set_kernel_events.restype = c_int32
     lib.fcsa_set_kernel_events.argtypes = [c_int32, c_void_p, c_void_p]
     _lib = lib

@@ -218,9 +218,24 @@ struct BwdArgs {
   // (dk_hat - k_hat <k_hat, dk_hat>_group) * rnorm_group is applied in the epilogue
   const float* k_rnorm;             // (B, H, Nk, G) or nullptr
   int G;                            // groups (group size D/G >= 8 when k_rnorm is set)
+  // additive bias on the logits (BIAS instantiation only): element type T, [b][h][query][key], element
+  // strides (bias_sb = 0: no batch dimension), keys contiguous.  dbias: fp32 accumulator of dS in the same
+  // index space ([.][.][Nq][Nk] planes, strides dbias_sb (0 = summed over the batch) / dbias_sh) or nullptr.
+  const void* bias; long long bias_sb, bias_sh, bias_sn;
+  float* dbias; long long dbias_sb, dbias_sh;
 };
 
-template <typename T, int D>
+// 16-bit global load through the read-only path (bias elements along the query axis are strided)
+__device__ __forceinline__ uint32_t ldg_u16(const void* p) {
+  uint16_t v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <typename T, int D, bool BIAS = false>
 __global__ void __launch_bounds__(640, 1)
 fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -625,6 +640,18 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // branch per element pair and starves the warp of instructions.
         uint32_t pk[CW / 2];                 // P^T packed; lives until the dS stage below
         uint32_t s[CW];
+        // bias[query][this key] of the CW queries, as packed pairs; the loads fly under the S^T wait
+        uint32_t bw[BIAS ? CW / 2 : 1];
+        if constexpr (BIAS) {
+          const uint8_t* bcol = reinterpret_cast<const uint8_t*>(a.bias) +
+                                2 * ((long long)b * a.bias_sb + (long long)h * a.bias_sh + min(key_g, a.Nk - 1));
+#pragma unroll
+          for (int e = 0; e < CW; e += 2) {
+            const int q0 = min(row0 + cq0 + e, a.Nq - 1), q1 = min(row0 + cq0 + e + 1, a.Nq - 1);
+            bw[e / 2] = ldg_u16(bcol + 2 * (long long)q0 * a.bias_sn) |
+                        (ldg_u16(bcol + 2 * (long long)q1 * a.bias_sn) << 16);
+          }
+        }
         ld_cw(tS, s);
         float c3v[AUG ? 2 : CW];
         if constexpr (!AUG) {
@@ -646,6 +673,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             float2 x;
             if constexpr (AUG) x = __fmul2_rn(sv, make_float2(c1, c1));     // the accumulator already holds s + c3/c1
             else x = __ffma2_rn(sv, make_float2(c1, c1), make_float2(c3v[AUG ? 0 : e], c3v[AUG ? 1 : e + 1]));
+            if constexpr (BIAS)
+              x = __ffma2_rn(unpack2<T>(bw[BIAS ? e / 2 : 0]), make_float2(1.4426950408889634f, 1.4426950408889634f), x);
             // some of the pairs on the FMA pipe (cubic minimax exp2), the rest on the MUFU
             const bool poly = FCSA_BWD_POLY_EVERY > 0 && ((e / 2) % (FCSA_BWD_POLY_EVERY > 0 ? FCSA_BWD_POLY_EVERY : 1)) == FCSA_BWD_POLY_EVERY - 1;
 #ifdef FCSA_EXP_NO_EXP
@@ -696,6 +725,15 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if constexpr (!AUG) t = __fadd2_rn(t, make_float2(dlv[AUG ? 0 : e], dlv[AUG ? 1 : e + 1]));  // delta stored negated
           const float2 v = __fmul2_rn(pa, t);
           ds[e / 2] = pack2<T>(v.x, v.y);
+          if constexpr (BIAS) {
+            // d bias = dS (reference cu:1574-1576): fp32 reduction, lanes = consecutive keys of one query row
+            if (a.dbias != nullptr && key_g < a.Nk) {
+              float* dst = a.dbias + (long long)b * a.dbias_sb + (long long)h * a.dbias_sh + key_g;
+              const int q0 = row0 + cq0 + e;
+              if (q0 < a.Nq) red_add_f32(dst + (long long)q0 * a.Nk, v.x);
+              if (q0 + 1 < a.Nq) red_add_f32(dst + (long long)(q0 + 1) * a.Nk, v.y);
+            }
+          }
         }
         // ---- dQ(i-1) out of its accumulator columns (its MMA sits right behind dK(i-1): long done;
         // it has also released the shared-memory dS^T), then dS^T(i) into them
@@ -1022,9 +1060,12 @@ struct BwdHostArgs {
   const float* q_rnorm = nullptr;
   const float* k_rnorm = nullptr;
   int groups = 1;
+  // additive bias (nullptr = none) and its fp32 gradient accumulator (nullptr = not needed)
+  const void* bias = nullptr; long long bias_sb = 0, bias_sh = 0, bias_sn = 0;
+  float* dbias = nullptr; long long dbias_sb = 0, dbias_sh = 0;
 };
 
-template <typename T, int D>
+template <typename T, int D, bool BIAS = false>
 int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, const char** err,
                    cudaError_t* ce) {
   using Cfg = BwdCfg<D>;
@@ -1098,7 +1139,9 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     a.dv = h.dv.ptr; a.dv_sb = h.dv.sb; a.dv_sh = h.dv.sh; a.dv_sn = h.dv.sn;
     a.k_rnorm = fuse_k ? h.k_rnorm : nullptr;
     a.G = h.groups;
-    auto kern = fcsa_bwd_kernel<T, D>;
+    a.bias = h.bias; a.bias_sb = h.bias_sb; a.bias_sh = h.bias_sh; a.bias_sn = h.bias_sn;
+    a.dbias = h.dbias; a.dbias_sb = h.dbias_sb; a.dbias_sh = h.dbias_sh;
+    auto kern = fcsa_bwd_kernel<T, D, BIAS>;
     static bool attr_set = false;
     if (!attr_set) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -1162,6 +1205,14 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
 
 inline int run_backward(const BwdHostArgs& h, cudaStream_t stream, int* launches, const char** err,
                         cudaError_t* ce) {
+  if (h.bias != nullptr) {
+    if (h.D == 64) {
+      if (h.dtype_bf16) return run_backward_t<__nv_bfloat16, 64, true>(h, stream, launches, err, ce);
+      return run_backward_t<__half, 64, true>(h, stream, launches, err, ce);
+    }
+    if (h.dtype_bf16) return run_backward_t<__nv_bfloat16, 128, true>(h, stream, launches, err, ce);
+    return run_backward_t<__half, 128, true>(h, stream, launches, err, ce);
+  }
   if (h.D == 64) {
     if (h.dtype_bf16) return run_backward_t<__nv_bfloat16, 64>(h, stream, launches, err, ce);
     return run_backward_t<__half, 64>(h, stream, launches, err, ce);

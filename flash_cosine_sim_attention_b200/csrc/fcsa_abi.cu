@@ -76,9 +76,19 @@ int check_problem(const fcsa_problem* p) {
   return FCSA_OK;
 }
 
-template <typename T, int D>
+int check_bias(const fcsa_problem* p, const fcsa_bias* bias) {
+  if (!bias || !bias->ptr) return fail(FCSA_ERR_INVALID, "attn_bias: null");
+  if (!aligned16(bias->ptr) || (bias->sn % 8) != 0 || (bias->sh % 8) != 0 || (bias->sb % 8) != 0)
+    return fail(FCSA_ERR_INVALID, "attn_bias: rows must be 16-byte aligned (strides multiples of 8 elements)");
+  if (bias->sn < ((p->seq_k + 7) / 8) * 8)
+    return fail(FCSA_ERR_INVALID, "attn_bias: row stride %lld shorter than seq_k rounded up to 8", (long long)bias->sn);
+  return FCSA_OK;
+}
+
+template <typename T, int D, bool BIAS = false>
 int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
-                   const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, cudaStream_t stream) {
+                   const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, cudaStream_t stream,
+                   const fcsa_bias* bias = nullptr) {
   using Cfg = fcsa::FwdCfg<D>;
   const bool bf = p->dtype == FCSA_BF16;
   CUtensorMap tq, tk, tv;
@@ -112,8 +122,12 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
   a.o_sh = o->sh;
   a.o_sn = o->sn;
   a.inv_l = inv_l;
+  a.bias = BIAS ? bias->ptr : nullptr;
+  a.bias_sb = BIAS ? bias->sb : 0;
+  a.bias_sh = BIAS ? bias->sh : 0;
+  a.bias_sn = BIAS ? bias->sn : 0;
 
-  auto kern = fcsa::fcsa_fwd_kernel<T, D>;
+  auto kern = fcsa::fcsa_fwd_kernel<T, D, BIAS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -201,6 +215,24 @@ int fcsa_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor*
   }
 }
 
+int fcsa_forward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                      const fcsa_tensor* v, const fcsa_bias* bias, const fcsa_tensor* o, float* inv_l,
+                      void* stream) {
+  int r;
+  if ((r = check_problem(p))) return r;
+  if ((r = check_tensor(q, "q")) || (r = check_tensor(k, "k")) || (r = check_tensor(v, "v")) ||
+      (r = check_tensor(o, "o")) || (r = check_bias(p, bias)))
+    return r;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (p->dtype == FCSA_BF16) {
+    if (p->head_dim == 64) return launch_forward<__nv_bfloat16, 64, true>(p, q, k, v, o, inv_l, s, bias);
+    return launch_forward<__nv_bfloat16, 128, true>(p, q, k, v, o, inv_l, s, bias);
+  } else {
+    if (p->head_dim == 64) return launch_forward<__half, 64, true>(p, q, k, v, o, inv_l, s, bias);
+    return launch_forward<__half, 128, true>(p, q, k, v, o, inv_l, s, bias);
+  }
+}
+
 size_t fcsa_backward_workspace_bytes(const fcsa_problem* p) {
   if (check_problem(p)) return 0;
   return fcsa::bwd_workspace_bytes(p->batch, p->heads, p->kv_heads, p->seq_q, p->seq_k, p->head_dim);
@@ -210,9 +242,12 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
                          const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
                          const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
                          const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream,
-                         const float* q_rnorm, const float* k_rnorm, int groups) {
+                         const float* q_rnorm, const float* k_rnorm, int groups,
+                         const fcsa_bias* bias = nullptr, float* d_bias_acc = nullptr, int64_t dsb = 0,
+                         int64_t dsh = 0) {
   int r;
   if ((r = check_problem(p))) return r;
+  if (bias && (r = check_bias(p, bias))) return r;
   if ((r = check_tensor(q, "q")) || (r = check_tensor(k, "k")) || (r = check_tensor(v, "v")) ||
       (r = check_tensor(o, "o")) || (r = check_tensor(d_o, "d_o")) || (r = check_tensor(dq, "dq")) ||
       (r = check_tensor(dk, "dk")) || (r = check_tensor(dv, "dv")))
@@ -237,6 +272,10 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
   h.q_rnorm = q_rnorm;
   h.k_rnorm = k_rnorm;
   h.groups = groups;
+  if (bias) {
+    h.bias = bias->ptr; h.bias_sb = bias->sb; h.bias_sh = bias->sh; h.bias_sn = bias->sn;
+    h.dbias = d_bias_acc; h.dbias_sb = dsb; h.dbias_sh = dsh;
+  }
   int launches = 0;
   const char* err = nullptr;
   cudaError_t ce = cudaSuccess;
@@ -253,6 +292,16 @@ int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor
                   const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream) {
   return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, stream,
                        nullptr, nullptr, 1);
+}
+
+int fcsa_backward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                       const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
+                       const float* inv_l, const fcsa_bias* bias, float* d_bias_acc, int64_t dsb,
+                       int64_t dsh, const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!bias) return fail(FCSA_ERR_INVALID, "attn_bias: null");
+  return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, stream,
+                       nullptr, nullptr, 1, bias, d_bias_acc, dsb, dsh);
 }
 
 int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,

@@ -47,6 +47,11 @@ struct FwdArgs {
   void* o;
   long long o_sb, o_sh, o_sn;   // element strides of o (feature dim contiguous)
   float* inv_l;                 // (B, H, Nq) fp32, contiguous
+  // additive bias on the logits (reference py:312, cu:1168,1214): element type = q's, [b][h][i][j] with
+  // element strides (bias_sb = 0 when the bias has no batch dimension); rows are 16-byte aligned and
+  // hold at least ceil8(Nk) elements.  Only read by the BIAS instantiation.
+  const void* bias;
+  long long bias_sb, bias_sh, bias_sn;
 };
 
 template <int D>
@@ -63,7 +68,7 @@ struct FwdCfg {
   static constexpr int kThreads = 640;                // 16 softmax warps + 4 service warps
 };
 
-template <typename T, int D>
+template <typename T, int D, bool BIAS = false>
 __global__ void __launch_bounds__(640, 1)
 fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FwdArgs a) {
@@ -261,6 +266,26 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tO = lane_base + 256 + t * D;
     const int nt = n_t[t];
     const float c1 = a.c1, nc2 = -a.c2;
+    // bias row of this query (clamped for the padding rows of the last tile, which are never stored)
+    const T* brow = nullptr;
+    if constexpr (BIAS)
+      brow = reinterpret_cast<const T*>(a.bias) + (long long)b * a.bias_sb + (long long)h * a.bias_sh +
+             (long long)min(row_g, a.Nq - 1) * a.bias_sn;
+    // 32 bias values of chunk c (tile-relative columns [32 (2 half + c), +32)) as 16 packed words, already
+    // turned into the addend of the exponent: bias * log2(e) - c2
+    auto bias_chunk = [&](int col0, int c, float2 (&bb)[16]) {
+      const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f), c2v = make_float2(nc2, nc2);
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        const int col = col0 + (2 * half + c) * 32 + 8 * v4;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (col < a.Nk) w = ldg_stream128(brow + col);
+        bb[4 * v4 + 0] = __ffma2_rn(unpack2<T>(w.x), l2e, c2v);
+        bb[4 * v4 + 1] = __ffma2_rn(unpack2<T>(w.y), l2e, c2v);
+        bb[4 * v4 + 2] = __ffma2_rn(unpack2<T>(w.z), l2e, c2v);
+        bb[4 * v4 + 3] = __ffma2_rn(unpack2<T>(w.w), l2e, c2v);
+      }
+    };
     float l = 0.f;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // two partial row-sum chains
 
@@ -300,9 +325,12 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const float2 c1v = make_float2(c1, c1), c2v = make_float2(nc2, nc2);
         auto chunk = [&](const uint32_t(&s)[32], int c) {
           uint32_t pk[16];
+          float2 bb[BIAS ? 16 : 1];
+          if constexpr (BIAS) bias_chunk(col0, c, bb);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c1v, c2v);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c1v,
+                                        BIAS ? bb[BIAS ? i : 0] : c2v);
             // every kPolyEvery-th pair goes to the FMA pipe instead of the MUFU
             const float2 pp = (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1)
                                   ? ex2_poly2(x)
@@ -340,9 +368,12 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const float2 c1v = make_float2(c1, c1), c2v = make_float2(nc2, nc2);
         auto chunk = [&](const uint32_t(&s)[32], int c, uint32_t v) {
           uint32_t pk[16];
+          float2 bb[BIAS ? 16 : 1];
+          if constexpr (BIAS) bias_chunk(col0, c, bb);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c1v, c2v);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c1v,
+                                        BIAS ? bb[BIAS ? i : 0] : c2v);
             const float p0 = ((v >> (2 * i)) & 1u) ? ex2_approx(x.x) : 0.f;
             const float p1 = ((v >> (2 * i + 1)) & 1u) ? ex2_approx(x.y) : 0.f;
             l += p0 + p1;

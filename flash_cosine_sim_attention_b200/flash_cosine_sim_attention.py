@@ -133,8 +133,29 @@ def _kernel_supported(q, k, v, attn_bias):
             and q.shape[-1] in _KERNEL_HEAD_DIMS and not exists(attn_bias))
 
 
-def _attn_forward(q, k, v, mask_u8, scale, shift, causal, need_inv_l=True):
-    """q, k (already normalised if wanted), v -> o, inv_l through fcsa_forward."""
+def _bias_ready(attn_bias, sh, dtype, batch_dim):
+    """(heads, i, j) - or (batch, i, j) when batch_dim - bias -> tensor in q's dtype whose rows are 16-byte
+    aligned (row length padded to a multiple of 8), plus the fcsa_bias struct addressing it as
+    [batch][head][i][j] (a stride of 0 for the dimension the bias does not have)."""
+    lead = sh.B if batch_dim else sh.H
+    assert tuple(attn_bias.shape) == (lead, sh.Nq, sh.Nk), \
+        f"attn_bias must be {(lead, sh.Nq, sh.Nk)} ({'batch' if batch_dim else 'heads'}, i, j), got {tuple(attn_bias.shape)}"
+    t = attn_bias.detach().to(dtype)
+    pad = (-sh.Nk) % 8
+    if pad:
+        t = torch.nn.functional.pad(t, (0, pad))
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    bs = _abi.FcsaBias()
+    bs.ptr = t.data_ptr()
+    plane = t.stride(0)
+    bs.sb, bs.sh, bs.sn = (plane, 0, t.stride(1)) if batch_dim else (0, plane, t.stride(1))
+    return t, bs
+
+
+def _attn_forward(q, k, v, mask_u8, scale, shift, causal, need_inv_l=True, bias=None, bias_batch_dim=False):
+    """q, k (already normalised if wanted), v -> o, inv_l through fcsa_forward (fcsa_forward_bias with a bias)."""
     lib = _abi.load()
     sh = _Shapes(q, k, v)
     q, k, v = _tma_ready(q), _tma_ready(k), _tma_ready(v)
@@ -143,12 +164,21 @@ def _attn_forward(q, k, v, mask_u8, scale, shift, causal, need_inv_l=True):
     p = _problem(sh, q.dtype, scale, shift, causal, mask_u8)
     tq, tk, tv, to = _view4(q, sh.qkind), _view4(k, sh.kkind), _view4(v, sh.kkind), _view4(o, sh.qkind)
     with torch.cuda.device(q.device):
-        _abi.check(lib.fcsa_forward(_abi.ref(p), _abi.ref(tq), _abi.ref(tk), _abi.ref(tv), _abi.ref(to),
-                                    inv_l.data_ptr() if need_inv_l else None, _stream(q.device)))
+        if bias is None:
+            _abi.check(lib.fcsa_forward(_abi.ref(p), _abi.ref(tq), _abi.ref(tk), _abi.ref(tv), _abi.ref(to),
+                                        inv_l.data_ptr() if need_inv_l else None, _stream(q.device)))
+        else:
+            keep, bs = _bias_ready(bias, sh, q.dtype, bias_batch_dim)
+            _abi.check(lib.fcsa_forward_bias(_abi.ref(p), _abi.ref(tq), _abi.ref(tk), _abi.ref(tv), _abi.ref(bs),
+                                             _abi.ref(to), inv_l.data_ptr() if need_inv_l else None,
+                                             _stream(q.device)))
+            del keep
     return o, inv_l
 
 
-def _attn_backward(do, o, inv_l, q, k, v, mask_u8, scale, shift, causal):
+def _attn_backward(do, o, inv_l, q, k, v, mask_u8, scale, shift, causal, bias=None, bias_batch_dim=False,
+                   bias_grad=False):
+    """-> dq, dk, dv (and d_bias, in the bias's dtype and shape, when bias_grad)."""
     lib = _abi.load()
     sh = _Shapes(q, k, v)
     q, k, v, o, do = _tma_ready(q), _tma_ready(k), _tma_ready(v), _tma_ready(o), _tma_ready(do)
@@ -162,12 +192,25 @@ def _attn_backward(do, o, inv_l, q, k, v, mask_u8, scale, shift, causal):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
     t = lambda x, kind: _view4(x, kind)
     with torch.cuda.device(q.device):
-        _abi.check(lib.fcsa_backward(
+        if bias is None:
+            _abi.check(lib.fcsa_backward(
+                _abi.ref(p), _abi.ref(t(q, sh.qkind)), _abi.ref(t(k, sh.kkind)), _abi.ref(t(v, sh.kkind)),
+                _abi.ref(t(o, sh.qkind)), _abi.ref(t(do, sh.qkind)), inv_l.data_ptr(),
+                _abi.ref(t(dq, sh.qkind)), _abi.ref(t(dk, sh.kkind)), _abi.ref(t(dv, sh.kkind)),
+                ws.data_ptr(), nbytes, _stream(q.device)))
+            return dq, dk, dv
+        keep, bs = _bias_ready(bias, sh, q.dtype, bias_batch_dim)
+        db_acc = torch.zeros(bias.shape, dtype=torch.float32, device=q.device) if bias_grad else None
+        plane = sh.Nq * sh.Nk
+        dsb, dsh = (plane, 0) if bias_batch_dim else (0, plane)
+        _abi.check(lib.fcsa_backward_bias(
             _abi.ref(p), _abi.ref(t(q, sh.qkind)), _abi.ref(t(k, sh.kkind)), _abi.ref(t(v, sh.kkind)),
-            _abi.ref(t(o, sh.qkind)), _abi.ref(t(do, sh.qkind)), inv_l.data_ptr(),
+            _abi.ref(t(o, sh.qkind)), _abi.ref(t(do, sh.qkind)), inv_l.data_ptr(), _abi.ref(bs),
+            db_acc.data_ptr() if bias_grad else None, dsb, dsh,
             _abi.ref(t(dq, sh.qkind)), _abi.ref(t(dk, sh.kkind)), _abi.ref(t(dv, sh.kkind)),
             ws.data_ptr(), nbytes, _stream(q.device)))
-    return dq, dk, dv
+        del keep
+    return dq, dk, dv, (db_acc.to(bias.dtype) if bias_grad else None)
 
 
 def _l2norm_struct(sh, groups, qn, kn, rq, rk):
@@ -257,24 +300,30 @@ def _l2norm_backward(dy, y, rnorm, groups):
 # the reference's extension-module surface: forward / backward / debug (cu:1630, 1752, 1921)
 # --------------------------------------------------------------------------------------------
 
-def forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal):
-    """Same contract as the reference's pybind `forward`: returns (o, inv_l, should_backwards)."""
-    if exists(attn_bias):
-        raise NotImplementedError("attn_bias is not implemented in the sm_100a kernels yet")
+def forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift=None):
+    """Same contract as the reference's pybind `forward`: returns (o, inv_l, should_backwards).
+    `shift` (extra, optional): the constant subtracted from the logits; the reference's is `scale`."""
     assert not (causal and exists(mask)), "mask should not be supplied if causality is needed"
     sh = _Shapes(q, k, v)
-    should_backwards = any(t.requires_grad for t in (q, k, v))
-    o, inv_l = _attn_forward(q, k, v, _prep_mask(mask, sh), scale, scale, causal, need_inv_l=True)
+    if sh.merged:
+        attn_bias_batch_dim = True          # reference cu:1647-1654
+    should_backwards = any(t.requires_grad for t in (q, k, v)) or (exists(attn_bias) and attn_bias.requires_grad)
+    o, inv_l = _attn_forward(q, k, v, _prep_mask(mask, sh), scale, scale if shift is None else shift, causal,
+                             need_inv_l=True, bias=attn_bias, bias_batch_dim=attn_bias_batch_dim)
     return o, inv_l, should_backwards
 
 
-def backward(d_out, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal):
+def backward(d_out, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift=None):
     """Same contract as the reference's pybind `backward`: returns (dq, dk, dv, db)."""
-    if exists(attn_bias):
-        raise NotImplementedError("attn_bias is not implemented in the sm_100a kernels yet")
     sh = _Shapes(q, k, v)
-    dq, dk, dv = _attn_backward(d_out, o, inv_l, q, k, v, _prep_mask(mask, sh), scale, scale, causal)
-    return dq, dk, dv, None
+    sft = scale if shift is None else shift
+    if not exists(attn_bias):
+        dq, dk, dv = _attn_backward(d_out, o, inv_l, q, k, v, _prep_mask(mask, sh), scale, sft, causal)
+        return dq, dk, dv, None
+    if sh.merged:
+        attn_bias_batch_dim = True
+    return _attn_backward(d_out, o, inv_l, q, k, v, _prep_mask(mask, sh), scale, sft, causal, bias=attn_bias,
+                          bias_batch_dim=attn_bias_batch_dim, bias_grad=attn_bias.requires_grad)
 
 
 def debug():
@@ -286,22 +335,22 @@ class FlashCosineSimAttention(Function):
     """The reference's autograd.Function (py:245-304) on already-normalised q, k."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim):
-        o, inv_l, should_backwards = forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal)
+    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim, shift=None):
+        o, inv_l, should_backwards = forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift)
         if not should_backwards:
             return o
         ctx.should_backwards = should_backwards
         ctx.save_for_backward(o, inv_l, q, k, v, mask, attn_bias)
-        ctx.params = (scale, causal, attn_bias_batch_dim)
+        ctx.params = (scale, causal, attn_bias_batch_dim, shift)
         return o
 
     @staticmethod
     def backward(ctx, do):
         assert ctx.should_backwards
         o, inv_l, q, k, v, mask, attn_bias = ctx.saved_tensors
-        scale, causal, attn_bias_batch_dim = ctx.params
-        dq, dk, dv, db = backward(do, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal)
-        return dq, dk, dv, None, db, None, None, None
+        scale, causal, attn_bias_batch_dim, shift = ctx.params
+        dq, dk, dv, db = backward(do, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift)
+        return dq, dk, dv, None, db, None, None, None, None
 
 
 flash_cosine_sim_attention_cuda = FlashCosineSimAttention.apply
@@ -468,8 +517,20 @@ def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
         o = _FusedCosineSimAttention.apply(pad(q), pad(k), pad(v), mask, float(scale), bool(causal), 1, False,
                                            int(groups) if l2norm_qk else 0)
         return o[..., :D]
+    if (exists(attn_bias) and q.dtype in _KERNEL_DTYPES and k.dtype == q.dtype and v.dtype == q.dtype
+            and D in _KERNEL_HEAD_DIMS and D % groups == 0 and attn_bias.is_cuda):
+        # additive bias: l2norm kernels (with their own backward), then the BIAS instantiations of the
+        # attention kernels; d_bias is reduced in fp32 and returned in the bias's dtype
+        if l2norm_qk:
+            q, k = l2norm_tensors(q, k, groups=groups)
+        shift = _choose_shift(q.dtype, scale, groups if l2norm_qk else 1, True)
+        if q.dtype == torch.float16:
+            # p = exp(logit - shift) is stored in fp16: keep its top below 2^15 whatever the bias adds
+            shift += max(float(attn_bias.detach().amax()), 0.0)
+        return FlashCosineSimAttention.apply(q, k, v, mask, attn_bias, float(scale), bool(causal),
+                                             bool(attn_bias_batch_dim), float(shift))
     if not _kernel_supported(q, k, v, attn_bias):
-        # float32 inputs, head dims above 128 / not a multiple of 8, and attn_bias have no sm_100a kernel yet:
+        # float32 inputs and head dims above 128 / not a multiple of 8 have no sm_100a kernel yet:
         # they run the un-fused formulation on the same GPU (correct, slower), never silently wrong.
         why = ("attn_bias" if exists(attn_bias) else
                f"dtype {q.dtype}" if q.dtype not in _KERNEL_DTYPES else f"head_dim {q.shape[-1]}")

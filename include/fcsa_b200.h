@@ -154,6 +154,33 @@ int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_
                         const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- additive attention bias -------------------------------------------------------------------
+ * Replaces the `attn_bias` / `attn_bias_batch_dim` arguments of the reference's forward / backward
+ * (flash_cosine_sim_attention_cuda.cu:1630-1639, 1752-1764; added to the logits at cu:1168,1214 and
+ * cu:1474-1476, gradient cu:1574-1576).  Elements have the problem's dtype; the bias is addressed as
+ * [batch][head][query][key] with ELEMENT strides sb (0 when the bias has no batch dimension -
+ * attn_bias_batch_dim == false), sh, sn and contiguous keys.  Rows must be 16-byte aligned: sb, sh, sn
+ * multiples of 8 and sn >= seq_k rounded up to 8 (pad the rows; the padding is never used). */
+typedef struct fcsa_bias {
+  const void* ptr;
+  int64_t sb, sh, sn;
+} fcsa_bias;
+
+/* fcsa_forward with the bias added to scale * q.k before the exponential. */
+int fcsa_forward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                      const fcsa_tensor* v, const fcsa_bias* bias, const fcsa_tensor* o, float* inv_l,
+                      void* stream);
+
+/* fcsa_backward with the bias.  d_bias_acc: fp32, zero-filled by the caller, same index space as the bias
+ * with element strides (dsb, dsh) over batch / head and contiguous [seq_q][seq_k] planes (dsb = 0 sums
+ * the gradient over the batch, as the reference does for a bias without batch dimension, cu:1574-1576);
+ * NULL when the bias needs no gradient (reference: db is empty unless it requires grad, cu:1827). */
+int fcsa_backward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
+                       const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
+                       const float* inv_l, const fcsa_bias* bias, float* d_bias_acc, int64_t dsb,
+                       int64_t dsh, const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /*
  * Measurement hook (bench.py roofline line; no reference counterpart - the reference only timed
  * whole calls, flash_cosine_sim_attention/benchmark.py:7-58).  While set, fcsa_forward (which = 0)

@@ -104,6 +104,42 @@ def test_padded_head_dims(fcsa, causal, mask, dim_head, groups, dtype):
           scale=8 if groups == 1 or dtype == torch.bfloat16 else 4)
 
 
+# ---- attn_bias (reference tests/test.py:32,58-61): the BIAS instantiations of both kernels, d_bias ----
+@pytest.mark.parametrize("causal,mask", [(True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("dim_head", [64, 128])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("batch_dim", [False, True])
+def test_attn_bias(fcsa, causal, mask, dim_head, dtype, batch_dim):
+    B, H, Nq, Nk = 2, 3, 150, 203            # ragged on both axes, Nk not a multiple of 8
+    if causal:
+        Nk = Nq
+    q, k, v, do, m = make_inputs((B, H, Nq, dim_head), (B, H, Nk, dim_head), dtype, seed=dim_head + 7 * batch_dim,
+                                 mask_p=0.4 if mask else None)
+    g = torch.Generator().manual_seed(99)
+    bias = torch.randn((B if batch_dim else H, Nq, Nk), generator=g).to(dtype)
+    if batch_dim:
+        # the reference's batch-dim bias is (batch, i, j): one plane shared by the heads of a batch element
+        pass
+    qd, kd, vd, bd = (t.cuda().requires_grad_() for t in (q, k, v, bias))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, mask=None if m is None else m.cuda(), attn_bias=bd,
+                                        causal=causal, attn_bias_batch_dim=batch_dim)
+    o.backward(do.cuda())
+    nb = bias.float().numpy()
+    if batch_dim:
+        # oracle indexes a batch-dim bias as bias[b]; it applies to every head of that batch element
+        ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(),
+                               mask=None if m is None else m.numpy(), attn_bias=nb, attn_bias_batch_dim=True,
+                               causal=causal, d_out=do.float().numpy(), empty_rows="zero", round_qk=ROUND[dtype])
+    else:
+        ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(),
+                               mask=None if m is None else m.numpy(), attn_bias=nb, causal=causal,
+                               d_out=do.float().numpy(), empty_rows="zero", round_qk=ROUND[dtype])
+    assert rel_err(o, ref[0]) <= TOL_OUT[dtype], "o"
+    for name, t, r in (("dq", qd, ref[1]), ("dk", kd, ref[2]), ("dv", vd, ref[3]), ("d_bias", bd, ref[4])):
+        assert t.grad is not None and t.grad.shape == t.shape and t.grad.dtype == dtype, name
+        assert rel_err(t.grad, r) <= TOL_GRAD[dtype], name
+
+
 # ---- committed golden vectors produced by the unmodified reference --------------------------------
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
