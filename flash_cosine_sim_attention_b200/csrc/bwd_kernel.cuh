@@ -9,25 +9,36 @@
 //     dK    = scale * dS^T q  dQ = scale * dS k            cu:1580-1610
 // The machine mapping is new.  Three kernels:
 //   1. bwd_prep_kernel    : per query row {c3 = log2(inv_l) - shift*log2e, delta} (fp32, never
-//                           rounded to 16 bit as the reference does at cu:1260/1820)
-//   2. fcsa_bwd_kernel    : one CTA per (key tile of 128, batch, head), key/value tile stationary
-//                           in shared memory, loop over query tiles of QT rows.  Everything is computed
-//                           TRANSPOSED (rows = keys): S^T = K Q^T and dP^T = V dO^T so that P^T and
-//                           dS^T land in TMEM exactly in the layout tcgen05 wants for an A operand
-//                           (dV += P^T dO, dK += dS^T Q read A from TMEM); dS is also staged in
-//                           shared memory for the dQ product.  dQ partial tiles leave through
-//                           shared memory and a TMA bulk reduce-add into an fp32 accumulator -
-//                           no per-element global atomics (reference: cu:1602-1610).
-//   3. bwd_dq_finish_kernel: fp32 accumulator * scale -> 16-bit dq.
+//                           rounded to 16 bit as the reference does at cu:1260/1820), for D = 64 also as
+//                           16-bit "slivers" (see 2.); zeroes the dQ accumulator
+//   2. fcsa_bwd_kernel    : one CTA per (key tile of 128, batch, head), key/value tile stationary,
+//                           loop over query tiles of QT rows.  Everything is computed TRANSPOSED
+//                           (rows = keys): S^T = K Q^T and dP^T = V dO^T so that P^T and dS^T land in
+//                           TMEM exactly in the layout tcgen05 wants for an A operand (dV += P^T dO,
+//                           dK += dS^T Q read A from TMEM); dS is also staged in shared memory for the
+//                           dQ product.  dQ partial tiles leave through shared memory and a TMA bulk
+//                           reduce-add into an fp32 accumulator - no per-element global atomics
+//                           (reference: cu:1602-1610).
+//   3. bwd_dq_finish_kernel: fp32 accumulator * scale -> 16-bit dq (+ l2norm backward of q).
+//
+// The main kernel is bound by shared-memory bandwidth (MMA operand fetch, TMA fills and the element-wise
+// warps' own traffic share 128 B/clk), so its structure minimises shared-memory accesses:
+//   * 16 compute warps, four per scheduler: warpgroup g owns a quarter of the query columns of every tile
+//     and runs the whole element-wise chain on them (S^T -> P^T -> dS^T -> drain of its dQ columns);
+//     P^T stays in registers between the exp and the dS step.
+//   * D = 64: the per-query constants are added INSIDE the accumulators by one extra K = 16 MMA step
+//     (ones[128x16] x sliver[QT x 16]^T, SWIZZLE_32B operands) - no shared-memory loads in the
+//     element-wise stage; K and V are copied into TMEM once per CTA, so S^T and dP^T are TS MMAs.
+//   * TMEM aliasing without long dependency chains: P^T over the dP^T columns its thread has read,
+//     dS^T into the dQ accumulator columns the same thread has just drained.
 //
 // Two shapes of the same kernel (TMEM has 512 columns; dV and dK need D each):
-//   D = 64 : QT = 128.  S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448) X [448,512)
+//   D = 64 : QT = 128.  S^T [0,128) dP^T/P^T [128,256) dV [256,320) dK [320,384) dQ/dS^T [384,448) K,V [448,512)
 //            dQ = dS K      (M = queries, A = dS from smem M-major, B = K)
-//   D = 128: QT = 64.   S^T [0,64)  dP^T [64,128)  dV [128,256) dK [256,384) dQ^T [384,448) X [448,480)
-//            dQ^T = K^T dS^T (M = features, A = K from smem M-major, B = dS^T)
-// X holds P^T (packed 16 bit), the TMEM A operand of dV; dS^T (the A operand of dK) is written
-// over the dP^T columns its producer has already consumed.  The two compute warpgroups form a
-// two-stage pipeline (exp stage on the MUFU pipe for tile i+1, dS stage on the FMA pipe for tile i).
+//   D = 128: QT = 64.   S^T [0,64)  dP^T/P^T [64,128)  dV [128,256) dK [256,384) dQ^T/dS^T [384,448)
+//            dQ^T = K^T dS^T (M = features, A = K from smem M-major, B = dS^T); constants from shared memory
+// BIAS instantiation: additive attention bias (16-bit loads along the query axis) and d_bias = dS
+// (fp32 reductions), reference cu:1474-1476 / 1574-1576.
 #pragma once
 
 #include <type_traits>

@@ -1,0 +1,19 @@
+import time, torch, sys
+sys.path.insert(0, '/root/repo')
+from flash_cosine_sim_attention_b200 import flash_cosine_sim_attention
+dev='cuda'
+for shape in [(4,8,4096,64),(1,8,512,64)]:
+    q,k,v,do=(torch.randn(shape,device=dev,dtype=torch.bfloat16) for _ in range(4))
+    q.requires_grad_();k.requires_grad_();v.requires_grad_()
+    def step():
+        o=flash_cosine_sim_attention(q,k,v,causal=True)
+        return torch.autograd.grad(o,(q,k,v),do)
+    for _ in range(10): step()
+    torch.cuda.synchronize()
+    n=200
+    t0=time.perf_counter()
+    for _ in range(n): step()
+    t1=time.perf_counter()
+    torch.cuda.synchronize()
+    t2=time.perf_counter()
+    print(shape, "enqueue us/step", (t1-t0)/n*1e6, "total us/step", (t2-t0)/n*1e6)
