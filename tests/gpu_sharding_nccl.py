@@ -18,7 +18,8 @@ from flash_cosine_sim_attention_b200.sharding import shard_range, sharded_flash_
 
 
 def relerr(a, b):
-    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6))
+    a, b = a.detach().float(), b.detach().float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
 
 
 def main():
