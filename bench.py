@@ -180,7 +180,7 @@ def main():
 
     # ---- device-resident timing -------------------------------------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]    # fwd s/e, bwd s/e
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(10)] for _ in range(K)]   # s/e of fwd, bwd, l2norm, prep, finish
     for row in kev:                                                                       # materialise handles
         for e in row:
             e.record()
@@ -188,21 +188,40 @@ def main():
     launches0 = debug()
     barrier()
     sampler.start()
+    # pass 1 - the headline: exactly K steps of the public API, nothing else on the stream between the
+    # five kernels of a step (an event recorded between two launches would turn their programmatic
+    # dependent launch back into a full serialisation)
+    # The host needs ~0.2 ms to enqueue a step and the device ~0.35 ms to run it, so the launch queue
+    # runs ahead of the device - except for the very first step after a barrier, whose kernels would be
+    # issued into an idle GPU one Python call at a time.  A ~1 ms spin kernel in front of the loop
+    # (outside every event pair) lets the queue fill first.
+    torch.cuda._sleep(2_000_000)
+    for _ in range(2):          # untimed: the device idled during the barrier / sampler start-up (clock ramp)
+        flush.zero_()
+        step(q, k, v, do)
     for i in range(K):
         flush.zero_()
-        lib.fcsa_set_kernel_events(0, kev[i][0].cuda_event, kev[i][1].cuda_event)
-        lib.fcsa_set_kernel_events(1, kev[i][2].cuda_event, kev[i][3].cuda_event)
         ev[i][0].record()
         step(q, k, v, do)
         ev[i][1].record()
     barrier()
     clocks = sampler.stop()
-    lib.fcsa_set_kernel_events(0, None, None)
-    lib.fcsa_set_kernel_events(1, None, None)
-    launches = debug() - launches0
+    launches = debug() - launches0 - 2 * 5      # the two untimed steps above
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    # pass 2 - the roofline numerators: the same K steps again with events recorded around exactly
+    # the forward and the backward tcgen05 kernel (library hook); not part of `value`
+    torch.cuda._sleep(2_000_000)
+    for i in range(K):
+        flush.zero_()
+        for w in range(5):
+            lib.fcsa_set_kernel_events(w, kev[i][2 * w].cuda_event, kev[i][2 * w + 1].cuda_event)
+        step(q, k, v, do)
+    barrier()
+    for w in range(5):
+        lib.fcsa_set_kernel_events(w, None, None)
     fwd_ms = [r[0].elapsed_time(r[1]) for r in kev]
     bwd_ms = [r[2].elapsed_time(r[3]) for r in kev]
+    aux_ms = [sum(r[2 * w].elapsed_time(r[2 * w + 1]) for r in kev) / K for w in (2, 3, 4)]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
 
     # ---- end to end from pinned host buffers ---------------------------------------------------
@@ -292,7 +311,13 @@ def main():
                              "ms": fwd_avg, "flops_per_launch": FWD_FLOPS},
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 4 * B * H * N * D * 2 * world,
                     "d2h_bytes_per_step": 4 * B * H * N * D * 2 * world, "ms_per_step": e2e_ms / K},
+            "step_breakdown_ms": {"l2norm_qk": aux_ms[0], "forward": fwd_avg, "preprocess": aux_ms[1],
+                                  "backward": bwd_avg, "dq_finish": aux_ms[2],
+                                  "note": "instrumented second pass (events between the launches); the "
+                                          "headline pass has none"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
+            "slowest_step_index": int(max(range(len(step_ms)), key=lambda j: step_ms[j])),
         }
         if world == 1 and not args.no_cpu_baseline:
             cpu_reference_sample(torch, 1)                        # warm-up

@@ -1066,6 +1066,7 @@ struct BwdHostArgs {
   const float* inv_l;
   void* workspace;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // optional: recorded around the main kernel
+  cudaEvent_t ev_prep[2] = {nullptr, nullptr}, ev_finish[2] = {nullptr, nullptr};   // ... the preprocess / dq finish
   // fused l2norm backward (q, k above are then the NORMALISED tensors and dq, dk the gradients
   // w.r.t. the raw ones); both null = plain backward
   const float* q_rnorm = nullptr;
@@ -1112,7 +1113,9 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     const int padded = w.nqt * Cfg::QT;
     dim3 grid((unsigned)((padded + rows_per_block - 1) / rows_per_block), (unsigned)(h.B * h.H));
     if (h.B * h.H > 65535) { *err = "batch*heads > 65535 not supported"; return FCSA_ERR_INVALID; }
+    if (h.ev_prep[0]) cudaEventRecord(h.ev_prep[0], stream);
     e = launch_pdl(bwd_prep_kernel<T>, grid, dim3(256), 0, stream, pa);
+    if (h.ev_prep[1]) cudaEventRecord(h.ev_prep[1], stream);
     if (e != cudaSuccess) { *err = "backward preprocess launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
   }
@@ -1173,12 +1176,14 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.dq_acc = dq_acc; fa.dq = h.dq.ptr; fa.sb = h.dq.sb; fa.sh = h.dq.sh; fa.sn = h.dq.sn;
     fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
     fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
+    if (h.ev_finish[0]) cudaEventRecord(h.ev_finish[0], stream);
     if (D == 64) {
       dim3 grid((unsigned)w.nqt, (unsigned)(h.B * h.H));
       e = launch_pdl(bwd_dq_finish64_kernel<T>, grid, dim3(256), 0, stream, fa);
     } else {
       e = launch_pdl(bwd_dq_finish128_kernel<T>, dim3((unsigned)((long long)h.B * h.H * w.nqt)), dim3(256), 0, stream, fa);
     }
+    if (h.ev_finish[1]) cudaEventRecord(h.ev_finish[1], stream);
     if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
     if (shared_kv) {

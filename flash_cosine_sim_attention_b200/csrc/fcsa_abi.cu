@@ -34,7 +34,7 @@ int sm_count() {
 }
 
 thread_local char g_err[512] = "";
-cudaEvent_t g_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+cudaEvent_t g_ev[5][2] = {};   // 0 forward, 1 backward, 2 l2norm(q,k), 3 backward preprocess, 4 dq finish
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -192,7 +192,8 @@ const char* fcsa_last_error(void) { return g_err; }
 int64_t fcsa_debug(void) { return g_launches.load(); }
 
 int fcsa_set_kernel_events(int32_t which, void* start_event, void* stop_event) {
-  if (which != 0 && which != 1) return fail(FCSA_ERR_INVALID, "which must be 0 (forward) or 1 (backward)");
+  if (which < 0 || which > 4)
+    return fail(FCSA_ERR_INVALID, "which must be 0 (forward), 1 (backward), 2 (l2norm), 3 (preprocess) or 4 (dq finish)");
   g_ev[which][0] = reinterpret_cast<cudaEvent_t>(start_event);
   g_ev[which][1] = reinterpret_cast<cudaEvent_t>(stop_event);
   return FCSA_OK;
@@ -269,6 +270,8 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
   h.workspace = workspace;
   h.ev_start = g_ev[1][0];
   h.ev_stop = g_ev[1][1];
+  h.ev_prep[0] = g_ev[3][0]; h.ev_prep[1] = g_ev[3][1];
+  h.ev_finish[0] = g_ev[4][0]; h.ev_finish[1] = g_ev[4][1];
   h.q_rnorm = q_rnorm;
   h.k_rnorm = k_rnorm;
   h.groups = groups;
@@ -342,6 +345,7 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   dim3 grid((unsigned)(items < persistent ? (items > 0 ? items : 1) : persistent));
   cudaError_t e;
   const bool bf = p->dtype == FCSA_BF16;
+  if (g_ev[2][0]) cudaEventRecord(g_ev[2][0], s);
   if (p->head_dim == 64)
     e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 8, U>, grid, dim3(256), 0, s, pa)
            : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 8, U>, grid, dim3(256), 0, s, pa);
@@ -351,6 +355,7 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   else
     e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 0, U>, grid, dim3(256), 0, s, pa)
            : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 0, U>, grid, dim3(256), 0, s, pa);
+  if (g_ev[2][1]) cudaEventRecord(g_ev[2][1], s);
   if (e != cudaSuccess) return cuda_fail(e, "l2norm (q, k) launch");
   g_launches.fetch_add(1);
   return fcsa_forward(p, &n->q_hat, &n->k_hat, v, o, inv_l, stream);

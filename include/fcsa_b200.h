@@ -186,7 +186,9 @@ int fcsa_backward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
  * whole calls, flash_cosine_sim_attention/benchmark.py:7-58).  While set, fcsa_forward (which = 0)
  * or fcsa_backward (which = 1) records the cudaEvent_t `start` / `stop` on the launch stream
  * immediately before / after its dominant kernel (the tcgen05 attention kernel, not the
- * pre/post passes).  Pass NULL, NULL to clear.  State is process-wide (autograd calls the
+ * pre/post passes); which = 2, 3, 4 do the same for the l2norm(q,k) pass of fcsa_forward_fused, the
+ * backward preprocess and the dq finish pass.  An event between two launches suspends their programmatic
+ * dependent launch, so a hooked run is for attribution, not for the headline time.  Pass NULL, NULL to clear.  State is process-wide (autograd calls the
  * backward from its own thread), so use it from single-stream measurement code only.
  */
 int fcsa_set_kernel_events(int32_t which, void* start_event, void* stop_event);
