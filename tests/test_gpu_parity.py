@@ -140,6 +140,42 @@ def test_attn_bias(fcsa, causal, mask, dim_head, dtype, batch_dim):
         assert rel_err(t.grad, r) <= TOL_GRAD[dtype], name
 
 
+def test_attn_bias_single_head_kv_grouped_l2norm(fcsa):
+    """bias together with shared keys/values (dk, dv summed over heads) and grouped l2norm, bf16."""
+    dtype = torch.bfloat16
+    B, H, Nq, Nk, D = 2, 4, 96, 136, 64
+    q, k, v, do, m = make_inputs((B, H, Nq, D), (B, Nk, D), dtype, seed=5, mask_p=0.3)
+    g = torch.Generator().manual_seed(6)
+    bias = torch.randn((H, Nq, Nk), generator=g).to(dtype)
+    qd, kd, vd, bd = (t.cuda().requires_grad_() for t in (q, k, v, bias))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, mask=m.cuda(), attn_bias=bd, groups=2, scale=6)
+    o.backward(do.cuda())
+    ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(), mask=m.numpy(),
+                           attn_bias=bias.float().numpy(), groups=2, scale=6, d_out=do.float().numpy(),
+                           empty_rows="zero", round_qk=ROUND[dtype])
+    assert rel_err(o, ref[0]) <= TOL_OUT[dtype], "o"
+    for name, t, r in (("dq", qd, ref[1]), ("dk", kd, ref[2]), ("dv", vd, ref[3]), ("d_bias", bd, ref[4])):
+        assert t.grad.shape == t.shape
+        assert rel_err(t.grad, r) <= TOL_GRAD[dtype], name
+
+
+def test_attn_bias_without_grad_and_forward_only(fcsa):
+    """a bias that needs no gradient takes the no-accumulator path; forward-only under no_grad."""
+    dtype = torch.float16
+    q, k, v, do, _ = make_inputs((1, 2, 200, 128), (1, 2, 200, 128), dtype, seed=8)
+    bias = torch.randn((2, 200, 200), generator=torch.Generator().manual_seed(9)).to(dtype)
+    ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(), attn_bias=bias.float().numpy(),
+                           causal=True, d_out=do.float().numpy(), empty_rows="zero", round_qk=ROUND[dtype])
+    with torch.no_grad():
+        o = fcsa.flash_cosine_sim_attention(q.cuda(), k.cuda(), v.cuda(), attn_bias=bias.cuda(), causal=True)
+    assert rel_err(o, ref[0]) <= TOL_OUT[dtype]
+    qd, kd, vd = (t.cuda().requires_grad_() for t in (q, k, v))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, attn_bias=bias.cuda(), causal=True)
+    o.backward(do.cuda())
+    for name, t, r in (("dq", qd, ref[1]), ("dk", kd, ref[2]), ("dv", vd, ref[3])):
+        assert rel_err(t.grad, r) <= TOL_GRAD[dtype], name
+
+
 # ---- committed golden vectors produced by the unmodified reference --------------------------------
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
