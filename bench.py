@@ -300,6 +300,8 @@ def main():
                        "global_batch": B * world, "seq_len": N, "heads": H, "head_dim": D,
                        "parallelism": f"batch-shard x{world} (no data-path collective)",
                        "l2": "256 MiB L2 flush between timed steps (outside the events)",
+                       "timing": "W warm-up steps, barrier+sync, 2 more untimed steps (clock ramp, launch queue), K steps "
+                                 "each between its own CUDA events, barrier+sync; max over ranks",
                        "flops_per_step_per_gpu": STEP_FLOPS},
             "frac_of_peak": value / world / peaks["bf16"], "peak_source": peaks["source"],
             "roofline": {"bound": "tensor", "kernel": "fcsa_bwd_kernel<bf16,64>", "achieved": ach,
