@@ -13,9 +13,16 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract; in short:
                (upload / compute / download on three streams, double-buffered across steps)
   roofline     the dominant kernel (the tcgen05 backward kernel), timed live with events recorded
                around exactly that launch, against the measured bf16 peak (MEASURED_PEAKS.json)
-  cpu_baseline the oracle's torch-f32 port of the reference's naive path on the host cores
+  cpu_baseline the reference's own naive path (plain_cosine_sim_attention, loaded unmodified by path when
+               a copy is present, else the oracle's port of it) on the host cores
+  c5           BASELINE config 5, (8,16,16384,128) bf16 causal, split over the N ranks by
+               flash_cosine_sim_attention_b200.sharding (batch first: 8/N batch elements per GPU), fwd+bwd,
+               plus - separately timed - the one NCCL all-gather of `o` a caller may ask for
 """
 import argparse
+import contextlib
+import importlib.util
+import io
 import json
 import os
 import subprocess
@@ -32,6 +39,8 @@ FWD_FLOPS = 4 * B * H * N * N * D / 2            # causal: half the score matrix
 BWD_FLOPS = 2.5 * FWD_FLOPS                      # 5 GEMMs vs 2
 STEP_FLOPS = FWD_FLOPS + BWD_FLOPS               # 2.405e11
 METRIC = "fwd+bwd TFLOP/s at (4,8,4096,64) bf16 causal"
+C5 = (8, 16, 16384, 128)
+C5_FLOPS = 3.5 * 4 * C5[0] * C5[1] * C5[2] * C5[2] * C5[3] / 2      # 3.079e13
 
 
 def load_peaks():
@@ -44,17 +53,20 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons of ONE GPU, sampled by one background process (rank 0 only:
+    eight pollers at 10 ms were part of the host-side contention seen at N = 8 in round 1).  It runs from
+    before the warm-up to after the last timed pass; rows are time-stamped on arrival and only those that
+    fall inside a marked window (the timed regions) are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -62,73 +74,123 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    @contextlib.contextmanager
+    def window(self):
+        t0 = time.perf_counter()
+        yield
+        self.windows.append((t0, time.perf_counter()))
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-            except ValueError:
-                continue
-            for nm, val in zip(names, r[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
+
+        def summarise(rows):
+            sm, mx, reasons = [], None, set()
+            for _, r in rows:
+                if len(r) < 6:
+                    continue
+                try:
+                    sm.append(float(r[0]))
+                    mx = float(r[1])
+                except ValueError:
+                    continue
+                for nm, val in zip(names, r[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            sm.sort()
+            return sm, mx, reasons
+        inside = [row for row in self.rows if any(a - 0.02 <= row[0] <= b + 0.02 for a, b in self.windows)]
+        sm, mx, reasons = summarise(inside)
+        scope = "timed regions"
+        if not sm:          # the timed regions are a few ms long: fall back to everything sampled under load
+            sm, mx, reasons = summarise(self.rows)
+            scope = "whole run (warm-up to last pass)"
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "scope": scope}
 
 
-def cpu_reference_sample(torch, heads):
-    """One bounded sample of the workload on the host: (1, heads, 4096, 64) f32 causal fwd+bwd through
-    the oracle's torch port of the reference's naive path.  Returns (seconds, flops)."""
+# ---------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU path on the host cores
+# ---------------------------------------------------------------------------------------------------
+REF_CANDIDATES = ("/root/reference/flash_cosine_sim_attention/flash_cosine_sim_attention.py",
+                  os.path.join(ROOT, "baseline", "_ref", "flash_cosine_sim_attention", "flash_cosine_sim_attention.py"))
+
+
+def load_reference_plain():
+    """The reference's plain_cosine_sim_attention, loaded UNMODIFIED by path (the package import itself
+    fails without its compiled extension).  (fn, "reference") or (oracle port, "port")."""
+    for path in REF_CANDIDATES:
+        if os.path.exists(path):
+            spec = importlib.util.spec_from_file_location("ref_fcsa_for_bench", path)
+            mod = importlib.util.module_from_spec(spec)
+            with contextlib.redirect_stdout(io.StringIO()):     # it prints a "not compiled" hint
+                spec.loader.exec_module(mod)
+            return mod.plain_cosine_sim_attention, "reference", path
     from oracle import cosine_sim_attention_oracle as oracle
+
+    def port(q, k, v, scale=8, groups=1, causal=False):
+        return oracle.torch_cpu_forward_backward(q, k, v, scale=scale, groups=groups, causal=causal, backward=False)
+    return port, "port", "oracle/cosine_sim_attention_oracle.py"
+
+
+def cpu_reference_sample(torch, fn, heads):
+    """One bounded sample of the workload on the host: (1, heads, 4096, 64) f32 causal fwd+bwd through the
+    reference's naive path.  Returns (seconds, flops)."""
     g = torch.Generator().manual_seed(0)
     q, k, v = (torch.randn(1, heads, N, D, generator=g).requires_grad_() for _ in range(3))
     t0 = time.perf_counter()
-    oracle.torch_cpu_forward_backward(q, k, v, scale=SCALE, groups=GROUPS, causal=True)
+    out = fn(q, k, v, scale=SCALE, groups=GROUPS, causal=True)
+    out.sum().backward()
     dt = time.perf_counter() - t0
     return dt, STEP_FLOPS * heads / (B * H)
 
 
+def host_threads(torch):
+    """All the host cores, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path (naive PyTorch ops on the
-    host cores; the reference is Python, so the oracle's torch port is what runs)."""
-    import torch
+    host cores).  Rank 0 alone runs it; the other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    cores = host_threads(torch)
+    fn, kind, src = load_reference_plain()
     heads = 2                                    # bounded sample: 1/16 of the workload per step
     for _ in range(max(args.warmup, 1)):
-        cpu_reference_sample(torch, heads)
+        cpu_reference_sample(torch, fn, heads)
     tot_t, tot_f = 0.0, 0.0
     for _ in range(args.steps):
-        dt, fl = cpu_reference_sample(torch, heads)
+        dt, fl = cpu_reference_sample(torch, fn, heads)
         tot_t += dt
         tot_f += fl
     val = tot_f / tot_t / 1e12
-    cores = torch.get_num_threads()
-    sample = f"(1,{heads},4096,64) f32 causal fwd+bwd per step = {heads}/{B*H} of the workload; {os.cpu_count()} logical cpus"
+    sample = (f"(1,{heads},4096,64) f32 causal fwd+bwd per step = {heads}/{B*H} of the workload, {src}; "
+              f"{os.cpu_count()} logical cpus")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3 * (B * H / heads),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "causal self-attn (4,8,4096,64) fwd+bwd, cosine-sim, scale 8", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "causal self-attn (4,8,4096,64) fwd+bwd, cosine-sim, scale 8", "sample": sample,
+                   "note": "ms_per_step is the time of ONE bounded sample; value = sample FLOPs / sample time"},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,22 +198,30 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (8,16,16384,128) sharded measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    import torch
-    import torch.distributed as dist
-    from flash_cosine_sim_attention_b200 import _abi, debug, flash_cosine_sim_attention
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # NCCL's INFO lines (version banner, "nranks N", NVLS/ring choice) go to stderr so the run can be
+        # checked for a real N-rank communicator; stdout stays one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+    import torch
+    import torch.distributed as dist
+    from flash_cosine_sim_attention_b200 import _abi, debug, flash_cosine_sim_attention
+    from flash_cosine_sim_attention_b200.sharding import shard_range, sharded_flash_cosine_sim_attention
+
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load()
     W = max(args.warmup, 3)
@@ -174,54 +244,57 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(W):
         step(q, k, v, do)
     barrier()
 
     # ---- device-resident timing -------------------------------------------------------------
+    NEV = 4                                      # l2norm(q,k), forward, preprocess, backward: the kernels of a step
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(10)] for _ in range(K)]   # s/e of fwd, bwd, l2norm, prep, finish
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * NEV)] for _ in range(K)]
     for row in kev:                                                                       # materialise handles
         for e in row:
             e.record()
-    sampler = ClockSampler(local)
     launches0 = debug()
     barrier()
-    sampler.start()
     # pass 1 - the headline: exactly K steps of the public API, nothing else on the stream between the
-    # five kernels of a step (an event recorded between two launches would turn their programmatic
-    # dependent launch back into a full serialisation)
-    # The host needs ~0.2 ms to enqueue a step and the device ~0.35 ms to run it, so the launch queue
-    # runs ahead of the device - except for the very first step after a barrier, whose kernels would be
-    # issued into an idle GPU one Python call at a time.  A ~1 ms spin kernel in front of the loop
-    # (outside every event pair) lets the queue fill first.
-    torch.cuda._sleep(2_000_000)
-    for _ in range(2):          # untimed: the device idled during the barrier / sampler start-up (clock ramp)
-        flush.zero_()
-        step(q, k, v, do)
-    for i in range(K):
-        flush.zero_()
-        ev[i][0].record()
-        step(q, k, v, do)
-        ev[i][1].record()
-    barrier()
-    clocks = sampler.stop()
-    launches = debug() - launches0 - 2 * 5      # the two untimed steps above
+    # kernels of a step (an event recorded between two launches would turn their programmatic dependent
+    # launch back into a full serialisation).  A ~1 ms spin kernel in front of the loop (outside every event
+    # pair) plus two untimed steps let the launch queue fill and the clocks ramp after the barrier.
+    with (sampler.window() if sampler else contextlib.nullcontext()):
+        torch.cuda._sleep(2_000_000)
+        for _ in range(2):
+            flush.zero_()
+            step(q, k, v, do)
+        host_t0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()
+            ev[i][0].record()
+            step(q, k, v, do)
+            ev[i][1].record()
+        host_enqueue_us = (time.perf_counter() - host_t0) / K * 1e6      # host time to ENQUEUE one step (no sync inside)
+        barrier()
+    launches_per_step = (debug() - launches0) // (K + 2)
+    launches = launches_per_step * K
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    # pass 2 - the roofline numerators: the same K steps again with events recorded around exactly
-    # the forward and the backward tcgen05 kernel (library hook); not part of `value`
-    torch.cuda._sleep(2_000_000)
-    for i in range(K):
-        flush.zero_()
-        for w in range(5):
-            lib.fcsa_set_kernel_events(w, kev[i][2 * w].cuda_event, kev[i][2 * w + 1].cuda_event)
-        step(q, k, v, do)
-    barrier()
+    # pass 2 - attribution: the same K steps again with events recorded around each kernel of the step
+    # (library hook); not part of `value`
+    which = {"l2norm_qk": 2, "forward": 0, "preprocess": 3, "backward": 1}
+    with (sampler.window() if sampler else contextlib.nullcontext()):
+        torch.cuda._sleep(2_000_000)
+        for i in range(K):
+            flush.zero_()
+            for slot, w in enumerate(which.values()):
+                lib.fcsa_set_kernel_events(w, kev[i][2 * slot].cuda_event, kev[i][2 * slot + 1].cuda_event)
+            step(q, k, v, do)
+        barrier()
     for w in range(5):
         lib.fcsa_set_kernel_events(w, None, None)
-    fwd_ms = [r[0].elapsed_time(r[1]) for r in kev]
-    bwd_ms = [r[2].elapsed_time(r[3]) for r in kev]
-    aux_ms = [sum(r[2 * w].elapsed_time(r[2 * w + 1]) for r in kev) / K for w in (2, 3, 4)]
+    parts = {name: sum(r[2 * slot].elapsed_time(r[2 * slot + 1]) for r in kev) / K for slot, name in enumerate(which)}
+    fwd_avg, bwd_avg = parts["forward"], parts["backward"]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
 
     # ---- end to end from pinned host buffers ---------------------------------------------------
@@ -267,35 +340,105 @@ def main():
     e2e_run(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for st in (s_up, s_cmp, s_dn):
-        st.wait_stream(torch.cuda.current_stream())
-    e2e_run(K)
-    e1.record()
-    barrier()
+    with (sampler.window() if sampler else contextlib.nullcontext()):
+        e0.record()
+        for st in (s_up, s_cmp, s_dn):
+            st.wait_stream(torch.cuda.current_stream())
+        e2e_run(K)
+        e1.record()
+        barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    del houts, dins, host
+
+    # ---- config 5: (8,16,16384,128) bf16 causal split over the ranks (SURVEY par. 8e) -------------------
+    c5 = None
+    if not args.no_c5:
+        Bc, Hc, Nc, Dc = C5
+        # every rank owns its batch elements (8 / world of the 8): generated per global batch index, so the
+        # union over ranks is the same problem at every N
+        lo, hi = shard_range(Bc, rank, world)
+
+        def gen(seed):
+            parts_ = []
+            for bi in range(lo, hi):
+                gc = torch.Generator(device=dev).manual_seed(1000 * seed + bi)
+                parts_.append(torch.randn(1, Hc, Nc, Dc, generator=gc, device=dev, dtype=dt))
+            return torch.cat(parts_, 0)
+        qc, kc, vc, dc = gen(1), gen(2), gen(3), gen(4)
+        qc.requires_grad_(), kc.requires_grad_(), vc.requires_grad_()
+
+        def c5_step():
+            o = sharded_flash_cosine_sim_attention(qc, kc, vc, causal=True, scale=SCALE, presharded=True)
+            grads = torch.autograd.grad(o, (qc, kc, vc), dc)
+            return o, grads
+        for _ in range(2):
+            c5_step()
+        barrier()
+        KC = max(3, min(K, 5))
+        cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KC)]
+        for i in range(KC):
+            cev[i][0].record()
+            o5, _ = c5_step()
+            cev[i][1].record()
+        barrier()
+        c5_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in cev) / KC], dtype=torch.float64, device=dev)
+        gather_ms, gather_ok = None, None
+        if world > 1:
+            # the one collective of the path, only when the caller wants the whole-batch output: an NCCL
+            # all-gather of o over NVLink, timed on its own and checked against the local shard
+            full = torch.empty(Bc, Hc, Nc, Dc, dtype=dt, device=dev)
+            o5c = o5.contiguous()
+            dist.all_gather_into_tensor(full, o5c)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                dist.all_gather_into_tensor(full, o5c)
+            g1.record()
+            barrier()
+            gm = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device=dev)
+            dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c5_ms, op=dist.ReduceOp.MAX)
+            gather_ms = float(gm.item())
+            ok = torch.tensor([int(torch.equal(full[lo:hi], o5c) and bool(torch.isfinite(full.float()).all())
+                                   and bool((full.float().abs().amax(dim=(1, 2, 3)) > 0).all()))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            gather_ok = bool(ok.item())
+            del full
+        c5_ms_f = float(c5_ms.item())
+        c5 = {"workload": f"(8,16,16384,128) bf16 causal fwd+bwd, batch split {Bc // world if Bc % world == 0 else '~' + str(Bc / world)} "
+                          f"per GPU x {world} (sharding.py, no data-path collective)",
+              "ms_per_step": c5_ms_f, "tflops": C5_FLOPS / (c5_ms_f * 1e-3) / 1e12, "steps": KC, "scaling": "strong",
+              "all_gather_o_ms": gather_ms, "all_gather_o_bytes": Bc * Hc * Nc * Dc * 2 if world > 1 else 0,
+              "all_gather_o_gbs_per_rank": (Bc * Hc * Nc * Dc * 2 * (world - 1) / world / (gather_ms * 1e-3) / 1e9)
+                                           if gather_ms else None,
+              "gathered_output_matches_local_shard": gather_ok}
+        del qc, kc, vc, dc, o5
 
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        he = torch.tensor([host_enqueue_us], dtype=torch.float64, device=dev)
+        dist.all_reduce(he, op=dist.ReduceOp.MAX)
+        host_enqueue_us = float(he.item())
     total_ms, e2e_ms = float(total_ms.item()), float(e2e_ms.item())
 
     if rank == 0:
+        clocks = sampler.stop()
         peaks = load_peaks()
         value = STEP_FLOPS * K * world / (total_ms * 1e-3) / 1e12
         e2e_val = STEP_FLOPS * K * world / (e2e_ms * 1e-3) / 1e12
-        bwd_avg = sum(bwd_ms) / K
-        fwd_avg = sum(fwd_ms) / K
         ach = BWD_FLOPS / (bwd_avg * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("fcsa_bwd_kernel_dram_bytes_per_launch")
+        aux = parts["l2norm_qk"] + parts["preprocess"]
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "causal self-attn (B,H,N,D)=(4,8,4096,64) per GPU, cosine-sim (l2norm fused), "
+            "config": {"workload": "causal self-attn (B,H,N,D)=(4,8,4096,64) per GPU, cosine-sim (l2norm of q,k inside the op), "
                                    "scale 8, fwd+bwd through flash_cosine_sim_attention()",
                        "global_batch": B * world, "seq_len": N, "heads": H, "head_dim": D,
                        "parallelism": f"batch-shard x{world} (no data-path collective)",
@@ -304,33 +447,37 @@ def main():
                                  "each between its own CUDA events, barrier+sync; max over ranks",
                        "flops_per_step_per_gpu": STEP_FLOPS},
             "frac_of_peak": value / world / peaks["bf16"], "peak_source": peaks["source"],
-            "roofline": {"bound": "tensor", "kernel": "fcsa_bwd_kernel<bf16,64>", "achieved": ach,
-                         "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": ach / peaks["bf16"], "traffic": traffic,
-                         "ms": bwd_avg, "flops_per_launch": BWD_FLOPS},
+            "roofline": {"bound": "tensor", "kernel": "fcsa_bwd_kernel<bf16,64> (incl. the fused dq conversion)",
+                         "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": ach / peaks["bf16"],
+                         "traffic": traffic, "ms": bwd_avg, "flops_per_launch": BWD_FLOPS},
             "roofline_fwd": {"bound": "tensor", "kernel": "fcsa_fwd_kernel<bf16,64>",
                              "achieved": FWD_FLOPS / (fwd_avg * 1e-3) / 1e12, "peak": peaks["bf16"],
                              "unit": "TFLOP/s", "frac": FWD_FLOPS / (fwd_avg * 1e-3) / 1e12 / peaks["bf16"],
                              "ms": fwd_avg, "flops_per_launch": FWD_FLOPS},
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 4 * B * H * N * D * 2 * world,
                     "d2h_bytes_per_step": 4 * B * H * N * D * 2 * world, "ms_per_step": e2e_ms / K},
-            "step_breakdown_ms": {"l2norm_qk": aux_ms[0], "forward": fwd_avg, "preprocess": aux_ms[1],
-                                  "backward": bwd_avg, "dq_finish": aux_ms[2],
-                                  "note": "instrumented second pass (events between the launches); the "
-                                          "headline pass has none"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "step_breakdown_ms": {**parts, "aux_total": aux,
+                                  "note": "instrumented second pass (events between the launches); the headline pass "
+                                          "has none.  The dq conversion (a separate 29 us pass in round 1) now runs "
+                                          "inside the backward kernel"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
+            "host_enqueue_us_per_step": host_enqueue_us, "clocks": clocks,
             "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
             "slowest_step_index": int(max(range(len(step_ms)), key=lambda j: step_ms[j])),
         }
+        if c5 is not None:
+            line["c5"] = c5
         if world == 1 and not args.no_cpu_baseline:
-            cpu_reference_sample(torch, 1)                        # warm-up
+            cores = host_threads(torch)
+            fn, kind, src = load_reference_plain()
+            cpu_reference_sample(torch, fn, 1)                        # warm-up
             t, f = 0.0, 0.0
             for _ in range(3):
-                a, b = cpu_reference_sample(torch, 2)
+                a, b = cpu_reference_sample(torch, fn, 2)
                 t, f = t + a, f + b
-            line["cpu_baseline"] = {"value": f / t / 1e12, "unit": "TFLOP/s", "cores": torch.get_num_threads(),
-                                    "kind": "port",
+            line["cpu_baseline"] = {"value": f / t / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": kind,
                                     "sample": "3 x (1,2,4096,64) f32 causal fwd+bwd (2/32 of the workload each), "
-                                              f"oracle torch port of the naive reference path, {os.cpu_count()} logical cpus"}
+                                              f"naive path of {src}, {os.cpu_count()} logical cpus"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "fcsa_debug",
     "fcsa_forward",
     "fcsa_backward_workspace_bytes",
+    "fcsa_backward_zeroed_bytes",
+    "fcsa_zeroed_init",
     "fcsa_backward",
     "fcsa_l2norm_forward",
     "fcsa_l2norm_backward",
@@ -66,7 +68,7 @@ class FcsaL2Norm(Structure):
 
 
 class FcsaBias(Structure):
-    _fields_ = [("ptr", c_void_p), ("sb", c_int64), ("sh", c_int64), ("sn", c_int64)]
+    _fields_ = [("ptr", c_void_p), ("sb", c_int64), ("sh", c_int64), ("sn", c_int64), ("amax", c_void_p)]
 
 
 class FcsaError(RuntimeError):
@@ -102,7 +104,12 @@ def load():
     lib.fcsa_backward_workspace_bytes.restype = c_size_t
     lib.fcsa_backward_workspace_bytes.argtypes = [PP]
     lib.fcsa_backward.restype = c_int32
-    lib.fcsa_backward.argtypes = [PP, PT, PT, PT, PT, PT, c_void_p, PT, PT, PT, c_void_p, c_size_t, c_void_p]
+    lib.fcsa_backward_zeroed_bytes.restype = c_size_t
+    lib.fcsa_backward_zeroed_bytes.argtypes = [PP]
+    lib.fcsa_zeroed_init.restype = c_int32
+    lib.fcsa_zeroed_init.argtypes = [c_void_p, c_size_t, c_void_p]
+    lib.fcsa_backward.argtypes = [PP, PT, PT, PT, PT, PT, c_void_p, PT, PT, PT, c_void_p, c_size_t, c_void_p, c_size_t,
+                                  c_void_p]
     lib.fcsa_l2norm_forward.restype = c_int32
     lib.fcsa_l2norm_forward.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, c_void_p]
     lib.fcsa_l2norm_backward.restype = c_int32
@@ -111,13 +118,14 @@ def load():
     lib.fcsa_forward_fused.restype = c_int32
     lib.fcsa_forward_fused.argtypes = [PP, PT, PT, PT, PN, PT, c_void_p, c_void_p]
     lib.fcsa_backward_fused.restype = c_int32
-    lib.fcsa_backward_fused.argtypes = [PP, PN, PT, PT, PT, c_void_p, PT, PT, PT, c_void_p, c_size_t, c_void_p]
+    lib.fcsa_backward_fused.argtypes = [PP, PN, PT, PT, PT, c_void_p, PT, PT, PT, c_void_p, c_size_t, c_void_p, c_size_t,
+                                        c_void_p]
     PB = POINTER(FcsaBias)
     lib.fcsa_forward_bias.restype = c_int32
     lib.fcsa_forward_bias.argtypes = [PP, PT, PT, PT, PB, PT, c_void_p, c_void_p]
     lib.fcsa_backward_bias.restype = c_int32
     lib.fcsa_backward_bias.argtypes = [PP, PT, PT, PT, PT, PT, c_void_p, PB, c_void_p, c_int64, c_int64,
-                                       PT, PT, PT, c_void_p, c_size_t, c_void_p]
+                                       PT, PT, PT, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
     lib.fcsa_set_kernel_events.restype = c_int32
     lib.fcsa_set_kernel_events.argtypes = [c_int32, c_void_p, c_void_p]
     _lib = lib

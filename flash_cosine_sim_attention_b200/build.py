@@ -1,10 +1,15 @@
-"""Builds libfcsa_b200.so (the C-ABI CUDA library) in-tree with nvcc, for sm_100a only.
+"""Builds the two native artefacts in-tree, for sm_100a only:
 
-Replaces the reference's setup.py CUDAExtension (setup.py:30-39), which passed no arch
-flags at all.  There is deliberately a single `-gencode`: this library has no other target.
+  libfcsa_b200.so                                  the C-ABI CUDA library (nvcc, one -gencode)
+  flash_cosine_sim_attention_cuda_0_1_40.*.so      the PyTorch extension module over that ABI (host C++
+                                                   compiler only) - the module the reference builds with
+                                                   its setup.py CUDAExtension (setup.py:30-39, no arch flags
+                                                   there) and imports by this versioned name (version.py:3)
 
-    python -m flash_cosine_sim_attention_b200.build        # build (skips if up to date)
+    python -m flash_cosine_sim_attention_b200.build        # build (skips what is up to date)
     python -m flash_cosine_sim_attention_b200.build -f     # force rebuild
+
+The repository's setup.py drives the same two steps for `pip install .` / `build_ext --inplace`.
 """
 import os
 import shutil
@@ -39,8 +44,64 @@ def _sources():
 def _deps():
     out = [os.path.join(ROOT, "include", "fcsa_b200.h")]
     for f in sorted(os.listdir(CSRC)):
-        out.append(os.path.join(CSRC, f))
+        if f.endswith((".cu", ".cuh", ".h")):
+            out.append(os.path.join(CSRC, f))
     return out
+
+
+# ---- the torch extension module ---------------------------------------------------------------------
+EXT_NAME = "flash_cosine_sim_attention_cuda_0_1_40"     # reference version.py:3 (__cuda_pkg_name__)
+EXT_SRC = os.path.join(CSRC, "torch_ext.cpp")
+
+
+def ext_path():
+    import sysconfig
+    return os.path.join(HERE, EXT_NAME + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def ext_compile_command(out=None):
+    """The g++ command line (list) that builds the extension module next to libfcsa_b200.so."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    cuda_home = os.environ.get("CUDA_HOME") or os.path.dirname(os.path.dirname(_nvcc()))
+    inc = list(ce.include_paths()) + [os.path.join(cuda_home, "include"), sysconfig.get_paths()["include"]]
+    libdirs = list(ce.library_paths()) + [os.path.join(cuda_home, "lib64")]
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+           f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    cmd += [f"-I{d}" for d in inc]
+    cmd += [EXT_SRC, "-o", out or ext_path()]
+    cmd += [f"-L{d}" for d in libdirs] + [f"-L{HERE}", "-l:libfcsa_b200.so"]
+    cmd += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
+    cmd += ["-Wl,-rpath,$ORIGIN"] + [f"-Wl,-rpath,{d}" for d in ce.library_paths()]
+    return cmd
+
+
+def ext_up_to_date():
+    out = ext_path()
+    if not os.path.exists(out):
+        return False
+    t = os.path.getmtime(out)
+    return all(os.path.getmtime(d) <= t for d in (EXT_SRC, os.path.join(ROOT, "include", "fcsa_b200.h")))
+
+
+def build_extension(force=False, verbose=False):
+    """Compile the torch extension module if needed (needs libfcsa_b200.so next to it); returns its path."""
+    build_library(force=False)
+    if not force and ext_up_to_date():
+        return ext_path()
+    cmd = ext_compile_command()
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    log = proc.stdout + proc.stderr
+    with open(os.path.join(HERE, "build_ext.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if proc.returncode != 0:
+        raise RuntimeError("extension build failed:\n" + log[-8000:])
+    if verbose:
+        print(log)
+    return ext_path()
 
 
 def up_to_date():
@@ -67,5 +128,5 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build_library(force="-f" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    print(build_library(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    print(build_extension(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -74,6 +74,15 @@ struct BwdCfg {
   //   aug S  : QT queries x 16, columns 0..2 = c3/c1 split in three 16-bit parts   (B operand)
   //   aug dP : QT queries x 16, columns 0..2 = -delta split in three 16-bit parts  (B operand)
   static constexpr bool kAug = (D == 64);
+  // D = 64: the dq finish pass runs inside the main kernel ("last CTA of a query tile converts it"); the
+  // list of tiles a CTA has to convert is a bitmap in the (otherwise unused) stats stages: 3 KB = 24576 tiles
+#ifdef FCSA_EXP_SKIP_REDUCE
+  static constexpr bool kFuseFinish = false;
+#else
+  static constexpr bool kFuseFinish = (D == 64);
+#endif
+  static constexpr int kProgressBytes = 64;               // 16 per-warp "tiles reduced" counters
+  static constexpr int kMaxFusedTiles = (3 * 1024 - kProgressBytes) * 8;
   static constexpr int kSliver = QT * 32;                 // bytes of one QT x 16 sliver
   static constexpr int kOffOnes = kOffStats + NST * 1024;
   static constexpr int kOffAug = kOffOnes + (kAug ? 4096 : 0);        // NST stages x {aug S, aug dP}
@@ -87,17 +96,26 @@ struct BwdCfg {
 };
 
 // ------------------------------------------------------------------------------------------
-// workspace layout (all fp32):
-//   stats : [B*H][nqt][2][QT]      c3 then -delta for each query tile (padded rows = 0)
-//   dq_acc: [B*H][nqt][4 warps][16 chunks][32 lanes][4]   32 KB per query tile, in the order the
-//           reduce warps produce it (D = 64: lane = query row, chunk = 4 features;
-//           D = 128: lane = feature, chunk = 4 query rows)
-//   dkv_acc (kv_heads == 1 < heads only): dk [B][Nk][D] then dv [B][Nk][D]
+// Two caller-provided device buffers:
+//
+// SCRATCH workspace (contents irrelevant on entry, garbage on exit):
+//   stats : fp32 [B*H][nqt][2][QT]   c3 then -delta for each query tile (padded rows = 0)
+//   dkv_acc (kv_heads == 1 < heads only): fp32 dk [B][Nk][D] then dv [B][Nk][D]
 //   aug   : 16-bit [B*H][nqt*QT][32]  cols 0..2 = c3/c1 in three parts, cols 16..18 = -delta in three
 //           parts, rest 0 (the extra K = 16 step of S^T and dP^T, D = 64); ones: 16-bit [128][16]
+//
+// ZEROED workspace (all zero on entry - the caller zero-fills it ONCE, fcsa_workspace_init - and all
+// zero again on exit: whoever converts an accumulator tile also clears it, so no per-call memset /
+// zeroing pass is needed; reference: a 33.5 MB cudaMemset of dq per backward, cu:1818):
+//   dq_acc: fp32 [B*H][nqt][4 warps][16 chunks][32 lanes][4]   32 KB per query tile, in the order the
+//           reduce warps produce it (D = 64: lane = query row, chunk = 4 features;
+//           D = 128: lane = feature, chunk = 4 query rows)
+//   cnt   : int32 [B*H][nqt]  arrivals per query tile (D = 64: the CTA that makes the count complete
+//           converts the tile inside the main kernel)
 // ------------------------------------------------------------------------------------------
 struct BwdWorkspace {
-  size_t stats_off, dq_off, dkv_off, aug_off, ones_off, total;
+  size_t stats_off, dkv_off, aug_off, ones_off, total;     // scratch
+  size_t dq_off, cnt_off, ztotal;                           // zeroed
   int nqt, QT;
 };
 
@@ -107,37 +125,47 @@ inline BwdWorkspace bwd_workspace_layout(int B, int H, int kv_heads, int Nq, int
   w.nqt = (Nq + w.QT - 1) / w.QT;
   size_t stats = (size_t)B * H * w.nqt * 2 * w.QT * 4;
   size_t dq = (size_t)B * H * w.nqt * 32768;
+  size_t cnt = (size_t)B * H * w.nqt * 4;
   size_t dkv = (kv_heads == 1 && H > 1) ? (size_t)2 * B * Nk * D * 4 : 0;
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   // augmented-contraction operands (16-bit): [B*H][nqt*QT][32] and the 128 x 16 ones tile
   size_t aug = (size_t)B * H * w.nqt * w.QT * 32 * 2;
   w.stats_off = 0;
-  w.dq_off = up(stats);
-  w.dkv_off = w.dq_off + up(dq);
+  w.dkv_off = up(stats);
   w.aug_off = w.dkv_off + up(dkv);
   w.ones_off = w.aug_off + up(aug);
   w.total = w.ones_off + 4096;
+  w.dq_off = 0;
+  w.cnt_off = up(dq);
+  w.ztotal = w.cnt_off + up(cnt);
   return w;
 }
 
 inline size_t bwd_workspace_bytes(int B, int H, int kv_heads, int Nq, int Nk, int D) {
   return bwd_workspace_layout(B, H, kv_heads, Nq, Nk, D).total;
 }
+inline size_t bwd_zeroed_workspace_bytes(int B, int H, int kv_heads, int Nq, int Nk, int D) {
+  return bwd_workspace_layout(B, H, kv_heads, Nq, Nk, D).ztotal;
+}
 
 // ------------------------------------------------------------------------------------------
 // 1. preprocess
 // ------------------------------------------------------------------------------------------
 struct PrepArgs {
-  int B, H, Nq, D, nqt, QT;
+  int B, H, Nq, Nk, D, nqt, QT, causal;
+  int bpb;                          // blocks per (batch, head): the grid is 1-D (no 65535 limit on batch*heads)
   float c2;                         // shift * log2e
+  const float* shift_extra;         // optional device scalar: shift += max(*shift_extra, 0) (bias range guard)
   const void* o;  long long o_sb, o_sh, o_sn;
   const void* d_o; long long do_sb, do_sh, do_sn;
   const float* inv_l;               // (B, H, Nq)
   float* stats;
-  float* dq_acc;                    // zeroed here (32 bytes per thread) instead of a separate memset
   void* aug;                        // 16-bit [B*H][nqt*QT][32] (see workspace layout) or nullptr
   void* ones;                       // 16-bit [128][16]
   float inv_c1;                     // 1 / (scale * log2e)
+  // fused dq finish (D = 64): query tiles that no key tile visits (causal with Nq > Nk) get their
+  // dq rows zeroed here, because no CTA of the main kernel will ever convert them
+  void* dq; long long dq_sb, dq_sh, dq_sn;
 };
 
 // x = p0 + p1 + p2 with each part representable in T (16 bit): 24 bits of x survive
@@ -151,52 +179,69 @@ __device__ __forceinline__ void split3(float x, uint32_t& w01, uint32_t& w2) {
   w2 = pack2<T>(e2, 0.f);
 }
 
+// number of key tiles (128 keys) whose CTA visits query tile qt = arrivals the tile's counter must see
+__host__ __device__ __forceinline__ int bwd_tile_contributors(int qt, int QT, int Nq, int Nk, int causal) {
+  const int nkt = (Nk + 127) >> 7;
+  if (!causal) return nkt;
+  const int last = qt * QT + QT - 1 + (Nk - Nq);      // last key column any row of the tile can see
+  if (last < 0) return 0;
+  const int c = (last >> 7) + 1;
+  return c < nkt ? c : nkt;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
-  // grid = (row blocks of the padded sequence, batch*heads); D/8 threads per row, 16-byte loads,
-  // shuffle reduce.  No per-thread integer division on the address path.
+  // 1-D grid = batch*heads x (row blocks of the padded sequence); D/8 threads per row, two rows per
+  // thread (four 16-byte loads in flight), shuffle reduce.  No per-thread integer division on the address path.
   pdl_launch_dependents();
   pdl_wait();
   const int tpr = a.D >> 3;
-  const int rows_per_block = 256 / tpr;
-  const int bh = blockIdx.y;
+  const int rpb = 256 / tpr;                 // rows per block and pass
+  const int bh = blockIdx.x / a.bpb;
+  const int blk = blockIdx.x - bh * a.bpb;
   const int b = bh / a.H, h = bh - b * a.H;
-  const int row = blockIdx.x * rows_per_block + threadIdx.x / tpr;     // row inside the padded (nqt*QT) range
   const int tr = threadIdx.x % tpr;
   const int padded = a.nqt * a.QT;
-  const bool in = row < padded;
-  const bool valid = in && row < a.Nq;
-  if (in) {
-    uint4* z = reinterpret_cast<uint4*>(a.dq_acc) + (((long long)bh * padded + row) * tpr + tr) * 2;
-    z[0] = make_uint4(0, 0, 0, 0);
-    z[1] = make_uint4(0, 0, 0, 0);
+  const float c2 = a.c2 + (a.shift_extra != nullptr ? fmaxf(__ldg(a.shift_extra), 0.f) * 1.4426950408889634f : 0.f);
+  int row[2];
+  bool in[2], valid[2];
+  uint4 ro[2], rd[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    row[u] = (blk * 2 + u) * rpb + threadIdx.x / tpr;     // row inside the padded (nqt*QT) range
+    in[u] = row[u] < padded;
+    valid[u] = in[u] && row[u] < a.Nq;
+    ro[u] = rd[u] = make_uint4(0, 0, 0, 0);
+    if (valid[u]) {
+      ro[u] = ldg_stream128(reinterpret_cast<const T*>(a.o) + b * a.o_sb + h * a.o_sh + (long long)row[u] * a.o_sn + tr * 8);
+      rd[u] = ldg_stream128(reinterpret_cast<const T*>(a.d_o) + b * a.do_sb + h * a.do_sh + (long long)row[u] * a.do_sn + tr * 8);
+    }
   }
-  float dot = 0.f;
-  if (valid) {
-    const T* op = reinterpret_cast<const T*>(a.o) + b * a.o_sb + h * a.o_sh + (long long)row * a.o_sn + tr * 8;
-    const T* dp = reinterpret_cast<const T*>(a.d_o) + b * a.do_sb + h * a.do_sh + (long long)row * a.do_sn + tr * 8;
-    const uint4 ro = *reinterpret_cast<const uint4*>(op);
-    const uint4 rd = *reinterpret_cast<const uint4*>(dp);
-    const float2 a0 = unpack2<T>(ro.x), a1 = unpack2<T>(ro.y), a2 = unpack2<T>(ro.z), a3 = unpack2<T>(ro.w);
-    const float2 b0 = unpack2<T>(rd.x), b1 = unpack2<T>(rd.y), b2 = unpack2<T>(rd.z), b3 = unpack2<T>(rd.w);
-    dot = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y +
-          a3.x * b3.x + a3.y * b3.y;
-  }
-  for (int m = 1; m < tpr; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
-  if (in && tr == 0) {
-    const int qt = row / a.QT, r = row - qt * a.QT;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float2 a0 = unpack2<T>(ro[u].x), a1 = unpack2<T>(ro[u].y), a2 = unpack2<T>(ro[u].z), a3 = unpack2<T>(ro[u].w);
+    const float2 b0 = unpack2<T>(rd[u].x), b1 = unpack2<T>(rd[u].y), b2 = unpack2<T>(rd[u].z), b3 = unpack2<T>(rd[u].w);
+    float dot = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y +
+                a3.x * b3.x + a3.y * b3.y;
+    for (int m = 1; m < tpr; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
+    if (!in[u]) continue;
+    const int qt = row[u] / a.QT, r = row[u] - qt * a.QT;
+    if (a.dq != nullptr && valid[u] && bwd_tile_contributors(qt, a.QT, a.Nq, a.Nk, a.causal) == 0)
+      *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.dq) + b * a.dq_sb + h * a.dq_sh + (long long)row[u] * a.dq_sn +
+                                tr * 8) = make_uint4(0, 0, 0, 0);
+    if (tr != 0) continue;
     float* st = a.stats + ((long long)bh * a.nqt + qt) * 2 * a.QT;
     float c3 = 0.f, dl = 0.f;
-    if (valid) {
-      c3 = log2f(a.inv_l[(long long)bh * a.Nq + row]) - a.c2;
+    if (valid[u]) {
+      c3 = log2f(a.inv_l[(long long)bh * a.Nq + row[u]]) - c2;
       dl = dot;
     }
     st[r] = c3;
     st[a.QT + r] = -dl;      // stored negated: the dS stage computes P * (dP + (-delta)) with packed adds
     if (a.aug) {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.aug) + ((long long)bh * padded + row) * 64);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.aug) + ((long long)bh * padded + row[u]) * 64);
       uint4 s0 = make_uint4(0, 0, 0, 0), d0 = s0;
-      if (valid) {
+      if (valid[u]) {
         split3<T>(c3 * a.inv_c1, s0.x, s0.y);
         split3<T>(-dl, d0.x, d0.y);
       }
@@ -204,7 +249,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
       dst[2] = d0; dst[3] = make_uint4(0, 0, 0, 0);
     }
   }
-  if (a.aug && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 128) {
+  if (a.aug && blockIdx.x == 0 && threadIdx.x < 128) {
     uint4* dst = reinterpret_cast<uint4*>(a.ones) + threadIdx.x * 2;
     const uint32_t one2 = pack2<T>(1.f, 1.f), one1 = pack2<T>(1.f, 0.f);
     dst[0] = make_uint4(one2, one1, 0, 0);
@@ -234,6 +279,12 @@ struct BwdArgs {
   // index space ([.][.][Nq][Nk] planes, strides dbias_sb (0 = summed over the batch) / dbias_sh) or nullptr.
   const void* bias; long long bias_sb, bias_sh, bias_sn;
   float* dbias; long long dbias_sb, dbias_sh;
+  // fused dq finish (D = 64): the CTA whose arrival completes a query tile's counter converts the fp32
+  // accumulator tile to 16-bit dq (x scale, optional l2norm backward w.r.t. the raw q) and clears it
+  int* cnt;                         // [B*H][nqt] arrivals, zero between launches
+  void* dq; long long dq_sb, dq_sh, dq_sn;
+  const void* q_hat; long long q_sb, q_sh, q_sn;   // normalised q (only read when q_rnorm is set)
+  const float* q_rnorm;             // (B, H, Nq, G) or nullptr
 };
 
 // 16-bit global load through the read-only path (bias elements along the query axis are strided)
@@ -244,6 +295,97 @@ __device__ __forceinline__ uint32_t ldg_u16(const void* p) {
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// 16-byte load served by L2 (never a stale L1 line): accumulator tiles other CTAs have reduced into
+__device__ __forceinline__ float4 ldg_cg128f(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+// Fused dq finish, D = 64 (replaces the separate finish pass; reference: the fp32 -> scalar_t cast of dq
+// after its atomics, cu:1904).  Accumulator tile = [4 row quarters][16 feature chunks][32 rows][4 features].
+// Called by every compute warp for the same tile: warp w converts rows [8w, 8w+8) - four adjacent
+// lanes share a row, 16 features each - so that group sums of the l2norm backward
+//     dq_raw = (dq_hat - q_hat <q_hat, dq_hat>_group) * rnorm_group            (py:38-65 + autograd)
+// are shuffles among those lanes.  The tile is read from L2, converted, and written back as zeros.
+template <typename T>
+__device__ __forceinline__ void finish_dq_tile64(const BwdArgs& a, int bh, int b, int h, int qt, int row, int part) {
+  float* tile = a.dq_acc + ((long long)bh * a.nqt + qt) * 8192;
+  const int wq = row >> 5, rl = row & 31;
+  float* src = tile + ((wq * 16 + 4 * part) * 32 + rl) * 4;
+  float4 acc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = ldg_cg128f(src + c * 128);
+  const int row_g = qt * 128 + row;
+  const bool ok = row_g < a.Nq;
+  const bool l2 = a.q_rnorm != nullptr;            // uniform across the grid
+  uint4 qraw[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  if (l2 && ok) {
+    const T* qp = reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh + (long long)row_g * a.q_sn + part * 16;
+    qraw[0] = ldg_stream128(qp);
+    qraw[1] = ldg_stream128(qp + 8);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(src + c * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+  float g[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    g[4 * c] = acc[c].x * a.scale; g[4 * c + 1] = acc[c].y * a.scale;
+    g[4 * c + 2] = acc[c].z * a.scale; g[4 * c + 3] = acc[c].w * a.scale;
+  }
+  if (l2) {
+    float y[16];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const float2 u0 = unpack2<T>(qraw[s2].x), u1 = unpack2<T>(qraw[s2].y), u2 = unpack2<T>(qraw[s2].z),
+                   u3 = unpack2<T>(qraw[s2].w);
+      y[8 * s2] = u0.x; y[8 * s2 + 1] = u0.y; y[8 * s2 + 2] = u1.x; y[8 * s2 + 3] = u1.y;
+      y[8 * s2 + 4] = u2.x; y[8 * s2 + 5] = u2.y; y[8 * s2 + 6] = u3.x; y[8 * s2 + 7] = u3.y;
+    }
+    const int gs = 64 / a.G;                       // features per group (power of two)
+    const long long rbase = (((long long)b * a.H + h) * a.Nq + (ok ? row_g : 0)) * a.G;
+    if (gs >= 8) {
+      float d0 = 0.f, d1 = 0.f;                    // <q_hat, dq_hat> over this thread's two 8-feature segments
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { d0 += y[i] * g[i]; d1 += y[8 + i] * g[8 + i]; }
+      if (gs >= 16) { d0 += d1; d1 = d0; }
+      if (gs >= 32) { d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, 1); d1 = d0; }
+      if (gs >= 64) { d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, 2); d1 = d0; }
+      const int seg0 = 2 * part;                   // 8-feature segment index of this thread's first half
+      const float r0 = ok ? a.q_rnorm[rbase + (seg0 * 8) / gs] : 0.f;
+      const float r1 = ok ? a.q_rnorm[rbase + (seg0 * 8 + 8) / gs] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[i] = (g[i] - y[i] * d0) * r0;
+        g[8 + i] = (g[8 + i] - y[8 + i] * d1) * r1;
+      }
+    } else {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        float pr[8], dot[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pr[i] = y[8 * s2 + i] * g[8 * s2 + i];
+        subgroup_sums8(pr, gs, dot);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float rn = ok ? a.q_rnorm[rbase + (part * 16 + 8 * s2 + i) / gs] : 0.f;
+          g[8 * s2 + i] = (g[8 * s2 + i] - y[8 * s2 + i] * dot[i]) * rn;
+        }
+      }
+    }
+  }
+  if (ok) {
+    T* dst = reinterpret_cast<T*>(a.dq) + b * a.dq_sb + h * a.dq_sh + (long long)row_g * a.dq_sn + part * 16;
+    uint4 o0, o1;
+    o0.x = pack2<T>(g[0], g[1]);   o0.y = pack2<T>(g[2], g[3]);   o0.z = pack2<T>(g[4], g[5]);   o0.w = pack2<T>(g[6], g[7]);
+    o1.x = pack2<T>(g[8], g[9]);   o1.y = pack2<T>(g[10], g[11]); o1.z = pack2<T>(g[12], g[13]); o1.w = pack2<T>(g[14], g[15]);
+    *reinterpret_cast<uint4*>(dst) = o0;
+    *reinterpret_cast<uint4*>(dst + 8) = o1;
+  }
 }
 
 template <typename T, int D, bool BIAS = false>
@@ -261,7 +403,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr uint32_t TM_S = Cfg::TM_S, TM_DP = Cfg::TM_DP, TM_DV = Cfg::TM_DV, TM_DK = Cfg::TM_DK,
                      TM_DQ = Cfg::TM_DQ, TM_X = Cfg::TM_X;
   constexpr bool KV_IN_TMEM = (D == 64);
-  constexpr bool AUG = Cfg::kAug;          // per-query constants enter through an extra K = 16 MMA step   // the X columns hold K (32 packed columns) and V (32): D = 64 only
+  constexpr bool AUG = Cfg::kAug;          // per-query constants enter through an extra K = 16 MMA step
+  constexpr bool FUSE_FINISH = Cfg::kFuseFinish;   // dq accumulator tiles are converted in this kernel
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -283,6 +426,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, KV_TMEM, DS_FULL,
     DQ_FULL, DKV_FULL, NBARS
   };
+  static_assert(NBARS * 8 + 4 <= 256, "barrier area");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -333,11 +477,17 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
+  if constexpr (FUSE_FINISH) {
+    if (warp == 19) {   // per-warp progress counters + bitmap of the tiles this CTA will convert
+      uint32_t* const z = reinterpret_cast<uint32_t*>(smem + Cfg::kOffStats);
+      for (int wi = lane; wi < Cfg::kProgressBytes / 4 + (NI + 31) / 32; wi += 32) z[wi] = 0u;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_wait();          // stats / zeroed dq accumulator come from the preprocess kernel
+  pdl_wait();          // slivers / stats come from the preprocess kernel; accumulators are zero on entry
 
   if (wg == 4) {
     reg_dealloc<64>();
@@ -536,6 +686,46 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_commit(BAR(DKV_FULL));
         }
       }
+    } else if (FUSE_FINISH && warp == 19) {
+      // =============================== tile tickets (fused dq finish) ==============
+      // progress[w] = number of query tiles whose bulk reduce-adds compute warp w has seen COMPLETE
+      // (cp.async.bulk.wait_group, not .read).  When all 16 warps are past tile j this warp draws one
+      // gpu-scope ticket for (CTA, tile j); the CTA that draws the last ticket of a tile owns its
+      // conversion: the tile goes into a bitmap the compute warps walk after their main loop.  No CTA
+      // ever waits for another one, and the compute warps never wait for this warp.
+      const uint32_t progress = sStats;
+      uint32_t* const won = reinterpret_cast<uint32_t*>(smem + Cfg::kOffStats + Cfg::kProgressBytes);
+      int next = 0;
+      while (next < NI) {
+        int done = 0x7FFFFFFF;
+        if (lane < 16) done = (int)ld_acquire_cta_shared(progress + 4 * lane);
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) done = min(done, __shfl_xor_sync(0xFFFFFFFFu, done, m));
+        done = __shfl_sync(0xFFFFFFFFu, done, 0);
+        if (done <= next) {
+          __nanosleep(200);
+          continue;
+        }
+        __syncwarp();
+        const int j = next + lane;
+        bool win = false;
+        if (j < done) {
+          const int qt = i_lo + j;
+          const int expected = bwd_tile_contributors(qt, QT, a.Nq, a.Nk, a.causal);
+          int* c = a.cnt + (long long)bh * a.nqt + qt;
+          __threadfence();                       // the 16 warps' completed reduce-adds happen-before the ticket
+          const int old = atomicAdd(c, 1);
+          win = (old == expected - 1);
+          if (win) {
+            __threadfence();                     // ... and every other CTA's before our reads of the tile
+            *c = 0;                              // nobody else touches this counter again in this launch
+            atomicOr(&won[j >> 5], 1u << (j & 31));
+          }
+        }
+        next = min(done, next + 32);
+      }
+      __syncwarp();
+      named_bar_sync(3, 512 + 32);              // bitmap complete -> compute warps
     }
   } else {
     // =============================== compute warpgroups =============================
@@ -595,6 +785,14 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float* dst = a.dq_acc + (((long long)bh * a.nqt + (i_lo + j)) * 4 + wq) * 2048 + wg * 512;
         bulk_reduce_add_f32(dst, my_stage, 2048);
         bulk_commit_group();
+        if constexpr (FUSE_FINISH) {
+          // the reduce of tile j-1 (issued one tile period ago) has fully landed: this warp's share of
+          // that tile is done
+          if (j > 0) {
+            bulk_wait_group<1>();
+            st_release_cta_shared(sStats + 4 * warp, (uint32_t)j);     // tiles [0, j) done by this warp
+          }
+        }
       }
 #endif
       if (tr_lane) FCSA_TR(3, j, 1);
@@ -770,8 +968,37 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         fence_proxy_async_smem();
         reduce_dq(NI - 1);
       }
-      if (lane == 0) bulk_wait_group<0>();
+      if (lane == 0) {
+        bulk_wait_group<0>();
+        if constexpr (FUSE_FINISH) {
+#ifndef FCSA_EXP_SKIP_REDUCE
+          if (NI > 0) st_release_cta_shared(sStats + 4 * warp, (uint32_t)NI);
+#endif
+        }
+      }
       __syncwarp();
+    }
+
+    // ---- fused dq finish: convert the query tiles whose last ticket this CTA drew ----------
+    // Every warp converts 8 rows of each such tile on its own (4 adjacent lanes = one row, 16 features
+    // each; group sums of the l2norm backward are shuffles among them), so nothing synchronises here.
+    if constexpr (FUSE_FINISH) {
+#ifndef FCSA_EXP_SKIP_REDUCE
+      if (NI > 0) {
+        named_bar_sync(3, 512 + 32);             // the ticket warp has filled the bitmap
+        const uint32_t* won = reinterpret_cast<const uint32_t*>(smem + Cfg::kOffStats + Cfg::kProgressBytes);
+        const int frow = warp * 8 + (lane >> 2);     // row inside the tile
+        const int fp = lane & 3;                     // which 16 of the 64 features
+        for (int w0 = 0; w0 < NI; w0 += 32) {
+          uint32_t bits = won[w0 >> 5];
+          while (bits) {
+            const int j = w0 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            finish_dq_tile64<T>(a, bh, b, h, i_lo + j, frow, fp);
+          }
+        }
+      }
+#endif
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
@@ -879,12 +1106,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. finish kernels
+// 3. finish kernels (D = 128 dq; shared-kv dk/dv)
 // ------------------------------------------------------------------------------------------
 struct DqFinishArgs {
   int B, H, Nq, D, nqt;
   float scale;
-  const float* dq_acc;
+  float* dq_acc;
   void* dq; long long sb, sh, sn;
   // when q_rnorm is set, dq is the gradient w.r.t. the RAW queries (l2norm backward applied here)
   const void* q_hat; long long q_sb, q_sh, q_sn;
@@ -927,61 +1154,10 @@ __device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishA
   }
 }
 
-// D = 64: accumulator tile = [4 warps][16 feature-chunks][32 rows][4 features].
-// One block = one query tile of 128 rows; one thread = 8 consecutive features of FOUR rows (one in
-// each warp-quarter of the tile), all twelve 16-byte loads issued before the first use.
-template <typename T>
-__global__ void __launch_bounds__(256) bwd_dq_finish64_kernel(const DqFinishArgs a) {
-  // grid = (query tiles, batch*heads); 8 threads per row
-  pdl_launch_dependents();
-  pdl_wait();
-  const int bh = blockIdx.y;
-  const int b = bh / a.H, h = bh - b * a.H;
-  const int c8 = threadIdx.x & 7;
-  const int rl = threadIdx.x >> 3;
-  const int qt = blockIdx.x;
-  const float* tile = a.dq_acc + ((long long)bh * a.nqt + qt) * 8192 + rl * 4;
-  float4 lo[4], hi[4];
-  uint4 qraw[4];
-  bool ok[4];
-  int row[4];
-  const bool l2 = a.q_rnorm != nullptr;          // uniform across the grid
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    row[w] = qt * 128 + w * 32 + rl;
-    ok[w] = row[w] < a.Nq;
-    lo[w] = hi[w] = make_float4(0, 0, 0, 0);
-    qraw[w] = make_uint4(0, 0, 0, 0);
-  }
-#pragma unroll
-  for (int w = 0; w < 4; ++w)
-    if (ok[w]) {
-      lo[w] = *reinterpret_cast<const float4*>(tile + w * 2048 + (2 * c8) * 128);
-      hi[w] = *reinterpret_cast<const float4*>(tile + w * 2048 + (2 * c8 + 1) * 128);
-      if (l2)
-        qraw[w] = ldg_stream128(reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh +
-                                (long long)row[w] * a.q_sn + c8 * 8);
-    }
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    float g[8];
-    g[0] = lo[w].x * a.scale; g[1] = lo[w].y * a.scale; g[2] = lo[w].z * a.scale; g[3] = lo[w].w * a.scale;
-    g[4] = hi[w].x * a.scale; g[5] = hi[w].y * a.scale; g[6] = hi[w].z * a.scale; g[7] = hi[w].w * a.scale;
-    finish_l2norm_bwd<T>(g, a, ok[w], qraw[w], b, h, ok[w] ? row[w] : 0, c8);
-    if (ok[w]) {
-      uint4 o4;
-      o4.x = pack2<T>(g[0], g[1]);
-      o4.y = pack2<T>(g[2], g[3]);
-      o4.z = pack2<T>(g[4], g[5]);
-      o4.w = pack2<T>(g[6], g[7]);
-      T* dst = reinterpret_cast<T*>(a.dq) + b * a.sb + h * a.sh + (long long)row[w] * a.sn + c8 * 8;
-      *reinterpret_cast<uint4*>(dst) = o4;
-    }
-  }
-}
-
 // D = 128: accumulator tile (64 query rows) = [4 warps][16 row-chunks][32 features][4 rows], i.e.
-// transposed.  One block = one tile: coalesced float4 loads -> shared memory -> row-major stores.
+// transposed.  One block = one tile: coalesced float4 loads -> shared memory -> row-major stores; the
+// tile is written back as zeros (the accumulator is zero between launches, see the workspace layout).
+// (D = 64 converts its tiles inside the main kernel: finish_dq_tile64.)
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArgs a) {
   __shared__ float tile[64][129];
@@ -991,9 +1167,10 @@ __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArg
   const int qt = (int)(unit % a.nqt);
   const int bh = (int)(unit / a.nqt);
   const int b = bh / a.H, h = bh % a.H;
-  const float* src = a.dq_acc + unit * 8192;
+  float* src = a.dq_acc + unit * 8192;
   for (int f = threadIdx.x; f < 2048; f += 256) {         // 2048 float4 per tile
     const float4 v = *reinterpret_cast<const float4*>(src + f * 4);
+    *reinterpret_cast<float4*>(src + f * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int wq = f >> 9, c = (f >> 5) & 15, ln = f & 31;
     const int d = wq * 32 + ln, r0 = c * 4;
     tile[r0 + 0][d] = v.x;
@@ -1064,7 +1241,8 @@ struct BwdHostArgs {
   const uint8_t* mask; long long mask_sb;
   fcsa_tensor q, k, v, o, d_o, dq, dk, dv;
   const float* inv_l;
-  void* workspace;
+  void* workspace;                  // scratch
+  void* zeroed;                     // zero on entry, zero again on exit (dq accumulator, tile counters)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // optional: recorded around the main kernel
   cudaEvent_t ev_prep[2] = {nullptr, nullptr}, ev_finish[2] = {nullptr, nullptr};   // ... the preprocess / dq finish
   // fused l2norm backward (q, k above are then the NORMALISED tensors and dq, dk the gradients
@@ -1074,6 +1252,7 @@ struct BwdHostArgs {
   int groups = 1;
   // additive bias (nullptr = none) and its fp32 gradient accumulator (nullptr = not needed)
   const void* bias = nullptr; long long bias_sb = 0, bias_sh = 0, bias_sn = 0;
+  const float* bias_amax = nullptr;           // optional device scalar added (if positive) to the shift
   float* dbias = nullptr; long long dbias_sb = 0, dbias_sh = 0;
 };
 
@@ -1083,16 +1262,22 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
   using Cfg = BwdCfg<D>;
   const BwdWorkspace w = bwd_workspace_layout(h.B, h.H, h.kv_heads, h.Nq, h.Nk, D);
   uint8_t* ws = reinterpret_cast<uint8_t*>(h.workspace);
+  uint8_t* zs = reinterpret_cast<uint8_t*>(h.zeroed);
   float* stats = reinterpret_cast<float*>(ws + w.stats_off);
-  float* dq_acc = reinterpret_cast<float*>(ws + w.dq_off);
+  float* dq_acc = reinterpret_cast<float*>(zs + w.dq_off);
+  int* cnt = reinterpret_cast<int*>(zs + w.cnt_off);
   float* dkv_acc = reinterpret_cast<float*>(ws + w.dkv_off);
   const bool shared_kv = (h.kv_heads == 1 && h.H > 1);
   const float log2e = 1.4426950408889634f;
   cudaError_t e;
+  if (Cfg::kFuseFinish && w.nqt > Cfg::kMaxFusedTiles) {
+    *err = "seq_q too long for the fused dq finish (more than 24064 query tiles)";
+    return FCSA_ERR_UNSUPPORTED;
+  }
 
-  // the dq accumulator is zeroed by the preprocess kernel; dk/dv accumulators (shared kv) here
+  // dk/dv accumulators of shared keys/values are per call (the dq accumulator is self-cleaning)
   if (shared_kv) {
-    e = cudaMemsetAsync(dkv_acc, 0, w.total - w.dkv_off, stream);
+    e = cudaMemsetAsync(dkv_acc, 0, (size_t)2 * h.B * h.Nk * D * 4, stream);
     if (e != cudaSuccess) { *err = "cudaMemsetAsync(workspace)"; *ce = e; return FCSA_ERR_CUDA; }
   }
   const int gs = D / (h.groups > 0 ? h.groups : 1);
@@ -1101,20 +1286,23 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
   // 1. preprocess
   {
     PrepArgs pa;
-    pa.B = h.B; pa.H = h.H; pa.Nq = h.Nq; pa.D = D; pa.nqt = w.nqt; pa.QT = Cfg::QT;
+    pa.B = h.B; pa.H = h.H; pa.Nq = h.Nq; pa.Nk = h.Nk; pa.D = D; pa.nqt = w.nqt; pa.QT = Cfg::QT; pa.causal = h.causal;
     pa.c2 = h.shift * log2e;
+    pa.shift_extra = h.bias_amax;
     pa.o = h.o.ptr; pa.o_sb = h.o.sb; pa.o_sh = h.o.sh; pa.o_sn = h.o.sn;
     pa.d_o = h.d_o.ptr; pa.do_sb = h.d_o.sb; pa.do_sh = h.d_o.sh; pa.do_sn = h.d_o.sn;
-    pa.inv_l = h.inv_l; pa.stats = stats; pa.dq_acc = dq_acc;
+    pa.inv_l = h.inv_l; pa.stats = stats;
     pa.aug = Cfg::kAug ? ws + w.aug_off : nullptr;
     pa.ones = ws + w.ones_off;
     pa.inv_c1 = 1.0f / (h.scale * log2e);
-    const int rows_per_block = 256 / (D / 8);
+    pa.dq = Cfg::kFuseFinish ? h.dq.ptr : nullptr; pa.dq_sb = h.dq.sb; pa.dq_sh = h.dq.sh; pa.dq_sn = h.dq.sn;
+    const int rows_per_block = 2 * (256 / (D / 8));
     const int padded = w.nqt * Cfg::QT;
-    dim3 grid((unsigned)((padded + rows_per_block - 1) / rows_per_block), (unsigned)(h.B * h.H));
-    if (h.B * h.H > 65535) { *err = "batch*heads > 65535 not supported"; return FCSA_ERR_INVALID; }
+    pa.bpb = (padded + rows_per_block - 1) / rows_per_block;
+    const long long grid = (long long)pa.bpb * h.B * h.H;
+    if (grid > 0x7FFFFFFFLL) { *err = "problem too large for one launch"; return FCSA_ERR_INVALID; }
     if (h.ev_prep[0]) cudaEventRecord(h.ev_prep[0], stream);
-    e = launch_pdl(bwd_prep_kernel<T>, grid, dim3(256), 0, stream, pa);
+    e = launch_pdl(bwd_prep_kernel<T>, dim3((unsigned)grid), dim3(256), 0, stream, pa);
     if (h.ev_prep[1]) cudaEventRecord(h.ev_prep[1], stream);
     if (e != cudaSuccess) { *err = "backward preprocess launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;
@@ -1126,7 +1314,8 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
         make_tensor_map_bhnd(&tk, h.k.ptr, h.dtype_bf16, h.B, h.kv_heads, h.Nk, D, h.k.sb, h.k.sh, h.k.sn, 128) ||
         make_tensor_map_bhnd(&tv, h.v.ptr, h.dtype_bf16, h.B, h.kv_heads, h.Nk, D, h.v.sb, h.v.sh, h.v.sn, 128) ||
         make_tensor_map_bhnd(&tdo, h.d_o.ptr, h.dtype_bf16, h.B, h.H, h.Nq, D, h.d_o.sb, h.d_o.sh, h.d_o.sn, Cfg::QT)) {
-      *err = "cuTensorMapEncodeTiled failed (backward)";
+      *err = "cuTensorMapEncodeTiled failed (backward): q, k, v, d_o must be views a TMA tensor map can express "
+             "(positive strides, 16-byte aligned)";
       return FCSA_ERR_INVALID;
     }
     // slivers of the augmented contraction: 16 columns x QT rows out of the [B*H][nqt*QT][32] tensor,
@@ -1155,13 +1344,13 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     a.G = h.groups;
     a.bias = h.bias; a.bias_sb = h.bias_sb; a.bias_sh = h.bias_sh; a.bias_sn = h.bias_sn;
     a.dbias = h.dbias; a.dbias_sb = h.dbias_sb; a.dbias_sh = h.dbias_sh;
+    a.cnt = cnt;
+    a.dq = h.dq.ptr; a.dq_sb = h.dq.sb; a.dq_sh = h.dq.sh; a.dq_sn = h.dq.sn;
+    a.q_hat = h.q.ptr; a.q_sb = h.q.sb; a.q_sh = h.q.sh; a.q_sn = h.q.sn;
+    a.q_rnorm = h.q_rnorm;
     auto kern = fcsa_bwd_kernel<T, D, BIAS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-      if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(bwd)"; *ce = e; return FCSA_ERR_CUDA; }
-      attr_set = true;
-    }
+    e = ensure_dynamic_smem<fcsa_bwd_kernel<T, D, BIAS>>(Cfg::kSmem);
+    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(bwd)"; *ce = e; return FCSA_ERR_CUDA; }
     const long long grid = (long long)((h.Nk + 127) / 128) * h.B * h.H;
     if (h.ev_start) cudaEventRecord(h.ev_start, stream);
     e = launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, tdo, taug, tones, a);
@@ -1176,16 +1365,13 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.dq_acc = dq_acc; fa.dq = h.dq.ptr; fa.sb = h.dq.sb; fa.sh = h.dq.sh; fa.sn = h.dq.sn;
     fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
     fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
-    if (h.ev_finish[0]) cudaEventRecord(h.ev_finish[0], stream);
-    if (D == 64) {
-      dim3 grid((unsigned)w.nqt, (unsigned)(h.B * h.H));
-      e = launch_pdl(bwd_dq_finish64_kernel<T>, grid, dim3(256), 0, stream, fa);
-    } else {
+    if (!Cfg::kFuseFinish) {           // D = 64 converts its dq tiles inside the main kernel
+      if (h.ev_finish[0]) cudaEventRecord(h.ev_finish[0], stream);
       e = launch_pdl(bwd_dq_finish128_kernel<T>, dim3((unsigned)((long long)h.B * h.H * w.nqt)), dim3(256), 0, stream, fa);
+      if (h.ev_finish[1]) cudaEventRecord(h.ev_finish[1], stream);
+      if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
+      ++*launches;
     }
-    if (h.ev_finish[1]) cudaEventRecord(h.ev_finish[1], stream);
-    if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
-    ++*launches;
     if (shared_kv) {
       for (int which = 0; which < 2; ++which) {
         KvFinishArgs ka;

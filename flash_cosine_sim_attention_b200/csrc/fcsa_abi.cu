@@ -22,13 +22,17 @@
 
 namespace {
 
-// SM count of the current device (persistent helper kernels size their grid from it)
+// SM count of the CURRENT device (persistent helper kernels size their grid from it); cached per
+// device, thread-safe (relaxed atomics: a race only repeats the query)
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[256];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool cacheable = dev >= 0 && dev < 256;
+  int n = cacheable ? cache[dev].load(std::memory_order_relaxed) : 0;
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cacheable) cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -56,6 +60,8 @@ int check_tensor(const fcsa_tensor* t, const char* name) {
   if (!aligned16(t->ptr)) return fail(FCSA_ERR_INVALID, "%s: pointer not 16-byte aligned", name);
   if ((t->sb % 8) || (t->sh % 8) || (t->sn % 8))
     return fail(FCSA_ERR_INVALID, "%s: strides must be multiples of 8 elements (16 bytes)", name);
+  if (t->sb < 0 || t->sh < 0 || t->sn < 0)
+    return fail(FCSA_ERR_INVALID, "%s: negative strides are not supported", name);
   return FCSA_OK;
 }
 
@@ -95,13 +101,13 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
   int r;
   if ((r = fcsa::make_tensor_map_bhnd(&tq, q->ptr, bf, p->batch, p->heads, p->seq_q, D, q->sb, q->sh,
                                       q->sn, 128)))
-    return fail(FCSA_ERR_CUDA, "cuTensorMapEncodeTiled(q) failed: %d", r);
+    return fail(r == -2 ? FCSA_ERR_INVALID : FCSA_ERR_CUDA, "q: %s (%d)", r == -2 ? "expanded (stride-0) views of extent > 1 cannot be addressed by a tensor map - make the tensor contiguous" : "cuTensorMapEncodeTiled failed", r);
   if ((r = fcsa::make_tensor_map_bhnd(&tk, k->ptr, bf, p->batch, p->kv_heads, p->seq_k, D, k->sb,
                                       k->sh, k->sn, 128)))
-    return fail(FCSA_ERR_CUDA, "cuTensorMapEncodeTiled(k) failed: %d", r);
+    return fail(r == -2 ? FCSA_ERR_INVALID : FCSA_ERR_CUDA, "k: %s (%d)", r == -2 ? "expanded (stride-0) views of extent > 1 cannot be addressed by a tensor map - make the tensor contiguous" : "cuTensorMapEncodeTiled failed", r);
   if ((r = fcsa::make_tensor_map_bhnd(&tv, v->ptr, bf, p->batch, p->kv_heads, p->seq_k, D, v->sb,
                                       v->sh, v->sn, 128)))
-    return fail(FCSA_ERR_CUDA, "cuTensorMapEncodeTiled(v) failed: %d", r);
+    return fail(r == -2 ? FCSA_ERR_INVALID : FCSA_ERR_CUDA, "v: %s (%d)", r == -2 ? "expanded (stride-0) views of extent > 1 cannot be addressed by a tensor map - make the tensor contiguous" : "cuTensorMapEncodeTiled failed", r);
 
   fcsa::FwdArgs a;
   a.B = p->batch;
@@ -126,13 +132,12 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
   a.bias_sb = BIAS ? bias->sb : 0;
   a.bias_sh = BIAS ? bias->sh : 0;
   a.bias_sn = BIAS ? bias->sn : 0;
+  a.bias_amax = BIAS ? bias->amax : nullptr;
 
   auto kern = fcsa::fcsa_fwd_kernel<T, D, BIAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+  {
+    cudaError_t e = fcsa::ensure_dynamic_smem<fcsa::fcsa_fwd_kernel<T, D, BIAS>>(Cfg::kSmem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fwd)");
-    attr_set = true;
   }
   const long long grid = (long long)a.n_qblk * p->batch * p->heads;
   if (grid > 0x7FFFFFFFLL) return fail(FCSA_ERR_INVALID, "problem too large for one launch");
@@ -185,7 +190,7 @@ int check_l2(int32_t dtype, int32_t B, int32_t H, int32_t N, int32_t D, int32_t 
 
 extern "C" {
 
-int fcsa_version(void) { return 100; }
+int fcsa_version(void) { return 200; }
 
 const char* fcsa_last_error(void) { return g_err; }
 
@@ -239,10 +244,23 @@ size_t fcsa_backward_workspace_bytes(const fcsa_problem* p) {
   return fcsa::bwd_workspace_bytes(p->batch, p->heads, p->kv_heads, p->seq_q, p->seq_k, p->head_dim);
 }
 
+size_t fcsa_backward_zeroed_bytes(const fcsa_problem* p) {
+  if (check_problem(p)) return 0;
+  return fcsa::bwd_zeroed_workspace_bytes(p->batch, p->heads, p->kv_heads, p->seq_q, p->seq_k, p->head_dim);
+}
+
+int fcsa_zeroed_init(void* zeroed, size_t bytes, void* stream) {
+  if (!zeroed || bytes == 0) return fail(FCSA_ERR_INVALID, "zeroed workspace: null / empty");
+  cudaError_t e = cudaMemsetAsync(zeroed, 0, bytes, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(zeroed workspace)");
+  return FCSA_OK;
+}
+
 static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
                          const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
                          const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
-                         const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream,
+                         const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* zeroed,
+                         size_t zeroed_bytes, void* stream,
                          const float* q_rnorm, const float* k_rnorm, int groups,
                          const fcsa_bias* bias = nullptr, float* d_bias_acc = nullptr, int64_t dsb = 0,
                          int64_t dsh = 0) {
@@ -258,6 +276,10 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
   if (!workspace || workspace_bytes < need)
     return fail(FCSA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   if (!aligned16(workspace)) return fail(FCSA_ERR_INVALID, "workspace not 16-byte aligned");
+  const size_t zneed = fcsa_backward_zeroed_bytes(p);
+  if (!zeroed || zeroed_bytes < zneed)
+    return fail(FCSA_ERR_WORKSPACE, "zeroed workspace too small: need %zu bytes, got %zu", zneed, zeroed_bytes);
+  if (!aligned16(zeroed)) return fail(FCSA_ERR_INVALID, "zeroed workspace not 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   fcsa::BwdHostArgs h;
   h.dtype_bf16 = p->dtype == FCSA_BF16;
@@ -268,6 +290,7 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
   h.q = *q; h.k = *k; h.v = *v; h.o = *o; h.d_o = *d_o; h.dq = *dq; h.dk = *dk; h.dv = *dv;
   h.inv_l = inv_l;
   h.workspace = workspace;
+  h.zeroed = zeroed;
   h.ev_start = g_ev[1][0];
   h.ev_stop = g_ev[1][1];
   h.ev_prep[0] = g_ev[3][0]; h.ev_prep[1] = g_ev[3][1];
@@ -277,6 +300,7 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
   h.groups = groups;
   if (bias) {
     h.bias = bias->ptr; h.bias_sb = bias->sb; h.bias_sh = bias->sh; h.bias_sn = bias->sn;
+    h.bias_amax = bias->amax;
     h.dbias = d_bias_acc; h.dbias_sb = dsb; h.dbias_sh = dsh;
   }
   int launches = 0;
@@ -292,19 +316,20 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
 int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
                   const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
                   const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
-                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream) {
-  return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, stream,
-                       nullptr, nullptr, 1);
+                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* zeroed,
+                  size_t zeroed_bytes, void* stream) {
+  return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, zeroed, zeroed_bytes,
+                       stream, nullptr, nullptr, 1);
 }
 
 int fcsa_backward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
                        const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
                        const float* inv_l, const fcsa_bias* bias, float* d_bias_acc, int64_t dsb,
                        int64_t dsh, const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       void* workspace, size_t workspace_bytes, void* zeroed, size_t zeroed_bytes, void* stream) {
   if (!bias) return fail(FCSA_ERR_INVALID, "attn_bias: null");
-  return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, stream,
-                       nullptr, nullptr, 1, bias, d_bias_acc, dsb, dsh);
+  return backward_impl(p, q, k, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes, zeroed, zeroed_bytes,
+                       stream, nullptr, nullptr, 1, bias, d_bias_acc, dsb, dsh);
 }
 
 int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
@@ -364,14 +389,15 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
 int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_tensor* v,
                         const fcsa_tensor* o, const fcsa_tensor* d_o, const float* inv_l,
                         const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        void* workspace, size_t workspace_bytes, void* zeroed, size_t zeroed_bytes,
+                        void* stream) {
   if (!n) return fail(FCSA_ERR_INVALID, "null fcsa_l2norm");
   int r;
   if ((r = check_problem(p))) return r;
   if ((r = check_l2(p->dtype, p->batch, p->heads, p->seq_q, p->head_dim, n->groups))) return r;
   if (!n->q_rnorm || !n->k_rnorm) return fail(FCSA_ERR_INVALID, "q_rnorm / k_rnorm: null");
   return backward_impl(p, &n->q_hat, &n->k_hat, v, o, d_o, inv_l, dq, dk, dv, workspace, workspace_bytes,
-                       stream, n->q_rnorm, n->k_rnorm, n->groups);
+                       zeroed, zeroed_bytes, stream, n->q_rnorm, n->k_rnorm, n->groups);
 }
 
 int fcsa_l2norm_forward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,

@@ -52,6 +52,7 @@ struct FwdArgs {
   // hold at least ceil8(Nk) elements.  Only read by the BIAS instantiation.
   const void* bias;
   long long bias_sb, bias_sh, bias_sn;
+  const float* bias_amax;       // optional device scalar: shift += max(*bias_amax, 0)  (fp16 range guard)
 };
 
 template <int D>
@@ -265,7 +266,11 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tP = (PSEP ? lane_base + 384 + t * 64 : lane_base + t * 128 + 64) + 32 * half;
     const uint32_t tO = lane_base + 256 + t * D;
     const int nt = n_t[t];
-    const float c1 = a.c1, nc2 = -a.c2;
+    float nc2 = -a.c2;
+    if constexpr (BIAS) {
+      if (a.bias_amax != nullptr) nc2 -= fmaxf(__ldg(a.bias_amax), 0.f) * 1.4426950408889634f;
+    }
+    const float c1 = a.c1;
     // bias row of this query (clamped for the padding rows of the last tile, which are never stored)
     const T* brow = nullptr;
     if constexpr (BIAS)

@@ -143,6 +143,16 @@ __device__ __forceinline__ uint4 ldg_stream128(const void* p) {
   return v;
 }
 
+// release / acquire on a shared-memory word (CTA scope): hand-off of plain counters between warps
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

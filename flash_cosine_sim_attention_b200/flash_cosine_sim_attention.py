@@ -25,7 +25,6 @@ import torch
 from torch.autograd import Function
 
 from . import _abi
-from ._abi import FcsaProblem, FcsaTensor
 
 __all__ = [
     "flash_cosine_sim_attention",
@@ -47,25 +46,22 @@ def exists(val):
 
 
 # --------------------------------------------------------------------------------------------
-# low level: tensors -> C ABI structs
+# host-side helpers mirrored in csrc/torch_ext.cpp (kept here for the sharding layer and the tests)
 # --------------------------------------------------------------------------------------------
 
 def _tma_ready(t):
     """Tensor usable behind a TMA tensor map as is: feature dim contiguous, 16-byte aligned
-    base and (batch, head, row) strides.  Otherwise a contiguous copy is made - e.g. for the
-    stride-0 expanded grad that `o.sum().backward()` produces."""
-    ok = t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and all(s % 8 == 0 for s in t.stride()[:-1])
+    base and (batch, head, row) strides, no stride-0 (expanded) dimension of extent > 1 - a tensor
+    map cannot express a broadcast.  Otherwise a contiguous copy is made - e.g. for the stride-0
+    expanded grad that `o.sum().backward()` / `o.sum(1)` produce, or head-expanded keys."""
+    ok = (t.stride(-1) == 1 and t.data_ptr() % 16 == 0
+          and all(s % 8 == 0 and (s > 0 or n == 1) for s, n in zip(t.stride()[:-1], t.shape[:-1])))
     return t if ok else t.contiguous()
 
 
-def _view4(t, kind):
-    """Canonical (batch, head, row, feature) addressing of a 3-D or 4-D tensor.
-    kind: 'bhnd' 4-D as is | 'bnd' 3-D (batch, row, feature) -> one head."""
-    if kind == "bhnd":
-        sb, sh, sn = t.stride(0), t.stride(1), t.stride(2)
-    else:
-        sb, sh, sn = t.stride(0), 0, t.stride(1)
-    return FcsaTensor(t.data_ptr(), sb, sh, sn)
+def _kernel_supported(q, k, v, attn_bias):
+    return (q.is_cuda and q.dtype in _KERNEL_DTYPES and k.dtype == q.dtype and v.dtype == q.dtype
+            and q.shape[-1] in _KERNEL_HEAD_DIMS and not exists(attn_bias))
 
 
 class _Shapes:
@@ -99,201 +95,46 @@ class _Shapes:
         assert v.shape[-2] == self.Nk
 
 
-def _problem(sh, dtype, scale, shift, causal, mask):
-    p = FcsaProblem()
-    p.dtype = _KERNEL_DTYPES[dtype]
-    p.batch, p.heads, p.kv_heads = sh.B, sh.H, sh.kv_heads
-    p.seq_q, p.seq_k, p.head_dim = sh.Nq, sh.Nk, sh.D
-    p.causal = 1 if causal else 0
-    p.scale = float(scale)
-    p.shift = float(shift)
-    if exists(mask):
-        p.key_mask = mask.data_ptr()
-        p.key_mask_stride = mask.stride(0)
+# --------------------------------------------------------------------------------------------
+# the compiled host layer: flash_cosine_sim_attention_cuda_0_1_40 (csrc/torch_ext.cpp), the
+# module the reference imports by this very name (py:15-20, version.py:3).  It canonicalises shapes,
+# allocates outputs and calls the C ABI on the current stream - a few microseconds per call.
+# --------------------------------------------------------------------------------------------
+_ext_module = None
+
+
+def _ext():
+    """Load (once) the torch extension module; registers it under its top-level name so that
+    `importlib.import_module('flash_cosine_sim_attention_cuda_0_1_40')` - what the reference's own
+    flash_cosine_sim_attention.py does - finds it too.  A missing build raises: no fallback."""
+    global _ext_module
+    if _ext_module is not None:
+        return _ext_module
+    import importlib.machinery
+    import importlib.util
+    import os
+    import sys
+    from .version import __cuda_pkg_name__ as name
+    if name in sys.modules:
+        _ext_module = sys.modules[name]
+        return _ext_module
+    here = os.path.dirname(os.path.abspath(__file__))
+    for suffix in importlib.machinery.EXTENSION_SUFFIXES:
+        path = os.path.join(here, name + suffix)
+        if os.path.exists(path):
+            break
     else:
-        p.key_mask = None
-        p.key_mask_stride = 0
-    return p
-
-
-def _stream(device):
-    return torch.cuda.current_stream(device).cuda_stream
-
-
-def _prep_mask(mask, sh):
-    if not exists(mask):
-        return None
-    assert mask.shape == (sh.B, sh.Nk), f"mask must be (batch, seq_k) = {(sh.B, sh.Nk)}, got {tuple(mask.shape)}"
-    m = mask.to(torch.bool).contiguous()
-    return m.view(torch.uint8)
-
-
-def _kernel_supported(q, k, v, attn_bias):
-    return (q.is_cuda and q.dtype in _KERNEL_DTYPES and k.dtype == q.dtype and v.dtype == q.dtype
-            and q.shape[-1] in _KERNEL_HEAD_DIMS and not exists(attn_bias))
-
-
-def _bias_ready(attn_bias, sh, dtype, batch_dim):
-    """(heads, i, j) - or (batch, i, j) when batch_dim - bias -> tensor in q's dtype whose rows are 16-byte
-    aligned (row length padded to a multiple of 8), plus the fcsa_bias struct addressing it as
-    [batch][head][i][j] (a stride of 0 for the dimension the bias does not have)."""
-    lead = sh.B if batch_dim else sh.H
-    assert tuple(attn_bias.shape) == (lead, sh.Nq, sh.Nk), \
-        f"attn_bias must be {(lead, sh.Nq, sh.Nk)} ({'batch' if batch_dim else 'heads'}, i, j), got {tuple(attn_bias.shape)}"
-    t = attn_bias.detach().to(dtype)
-    pad = (-sh.Nk) % 8
-    if pad:
-        t = torch.nn.functional.pad(t, (0, pad))
-    t = t.contiguous()
-    if t.data_ptr() % 16:
-        t = t.clone()
-    bs = _abi.FcsaBias()
-    bs.ptr = t.data_ptr()
-    plane = t.stride(0)
-    bs.sb, bs.sh, bs.sn = (plane, 0, t.stride(1)) if batch_dim else (0, plane, t.stride(1))
-    return t, bs
-
-
-def _attn_forward(q, k, v, mask_u8, scale, shift, causal, need_inv_l=True, bias=None, bias_batch_dim=False):
-    """q, k (already normalised if wanted), v -> o, inv_l through fcsa_forward (fcsa_forward_bias with a bias)."""
-    lib = _abi.load()
-    sh = _Shapes(q, k, v)
-    q, k, v = _tma_ready(q), _tma_ready(k), _tma_ready(v)
-    o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
-    inv_l = torch.empty((sh.B, sh.H, sh.Nq), dtype=torch.float32, device=q.device) if need_inv_l else None
-    p = _problem(sh, q.dtype, scale, shift, causal, mask_u8)
-    tq, tk, tv, to = _view4(q, sh.qkind), _view4(k, sh.kkind), _view4(v, sh.kkind), _view4(o, sh.qkind)
-    with torch.cuda.device(q.device):
-        if bias is None:
-            _abi.check(lib.fcsa_forward(_abi.ref(p), _abi.ref(tq), _abi.ref(tk), _abi.ref(tv), _abi.ref(to),
-                                        inv_l.data_ptr() if need_inv_l else None, _stream(q.device)))
-        else:
-            keep, bs = _bias_ready(bias, sh, q.dtype, bias_batch_dim)
-            _abi.check(lib.fcsa_forward_bias(_abi.ref(p), _abi.ref(tq), _abi.ref(tk), _abi.ref(tv), _abi.ref(bs),
-                                             _abi.ref(to), inv_l.data_ptr() if need_inv_l else None,
-                                             _stream(q.device)))
-            del keep
-    return o, inv_l
-
-
-def _attn_backward(do, o, inv_l, q, k, v, mask_u8, scale, shift, causal, bias=None, bias_batch_dim=False,
-                   bias_grad=False):
-    """-> dq, dk, dv (and d_bias, in the bias's dtype and shape, when bias_grad)."""
-    lib = _abi.load()
-    sh = _Shapes(q, k, v)
-    q, k, v, o, do = _tma_ready(q), _tma_ready(k), _tma_ready(v), _tma_ready(o), _tma_ready(do)
-    dq = torch.empty(q.shape, dtype=q.dtype, device=q.device)
-    dk = torch.empty(k.shape, dtype=k.dtype, device=q.device)
-    dv = torch.empty(v.shape, dtype=v.dtype, device=q.device)
-    p = _problem(sh, q.dtype, scale, shift, causal, mask_u8)
-    nbytes = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
-    if nbytes == 0:
-        _abi.check(_abi.FCSA_ERR_INVALID)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
-    t = lambda x, kind: _view4(x, kind)
-    with torch.cuda.device(q.device):
-        if bias is None:
-            _abi.check(lib.fcsa_backward(
-                _abi.ref(p), _abi.ref(t(q, sh.qkind)), _abi.ref(t(k, sh.kkind)), _abi.ref(t(v, sh.kkind)),
-                _abi.ref(t(o, sh.qkind)), _abi.ref(t(do, sh.qkind)), inv_l.data_ptr(),
-                _abi.ref(t(dq, sh.qkind)), _abi.ref(t(dk, sh.kkind)), _abi.ref(t(dv, sh.kkind)),
-                ws.data_ptr(), nbytes, _stream(q.device)))
-            return dq, dk, dv
-        keep, bs = _bias_ready(bias, sh, q.dtype, bias_batch_dim)
-        db_acc = torch.zeros(bias.shape, dtype=torch.float32, device=q.device) if bias_grad else None
-        plane = sh.Nq * sh.Nk
-        dsb, dsh = (plane, 0) if bias_batch_dim else (0, plane)
-        _abi.check(lib.fcsa_backward_bias(
-            _abi.ref(p), _abi.ref(t(q, sh.qkind)), _abi.ref(t(k, sh.kkind)), _abi.ref(t(v, sh.kkind)),
-            _abi.ref(t(o, sh.qkind)), _abi.ref(t(do, sh.qkind)), inv_l.data_ptr(), _abi.ref(bs),
-            db_acc.data_ptr() if bias_grad else None, dsb, dsh,
-            _abi.ref(t(dq, sh.qkind)), _abi.ref(t(dk, sh.kkind)), _abi.ref(t(dv, sh.kkind)),
-            ws.data_ptr(), nbytes, _stream(q.device)))
-        del keep
-    return dq, dk, dv, (db_acc.to(bias.dtype) if bias_grad else None)
-
-
-def _l2norm_struct(sh, groups, qn, kn, rq, rk):
-    n = _abi.FcsaL2Norm()
-    n.groups = groups
-    n.q_hat, n.k_hat = _view4(qn, sh.qkind), _view4(kn, sh.kkind)
-    n.q_rnorm, n.k_rnorm = rq.data_ptr(), rk.data_ptr()
-    return n
-
-
-def _attn_forward_fused(q, k, v, mask_u8, scale, shift, causal, groups, need_inv_l=True):
-    """raw q, k -> (o, inv_l, q_hat, k_hat, q_rnorm, k_rnorm) through fcsa_forward_fused: one
-    launch normalises q and k, one runs the attention."""
-    lib = _abi.load()
-    sh = _Shapes(q, k, v)
-    q, k, v = _tma_ready(q), _tma_ready(k), _tma_ready(v)
-    dev = q.device
-    o = torch.empty(q.shape, dtype=q.dtype, device=dev)
-    qn = torch.empty(q.shape, dtype=q.dtype, device=dev)
-    kn = torch.empty(k.shape, dtype=k.dtype, device=dev)
-    rq = torch.empty((sh.B, sh.H, sh.Nq, groups), dtype=torch.float32, device=dev)
-    rk = torch.empty((sh.B, sh.kv_heads, sh.Nk, groups), dtype=torch.float32, device=dev)
-    inv_l = torch.empty((sh.B, sh.H, sh.Nq), dtype=torch.float32, device=dev) if need_inv_l else None
-    p = _problem(sh, q.dtype, scale, shift, causal, mask_u8)
-    n = _l2norm_struct(sh, groups, qn, kn, rq, rk)
-    with torch.cuda.device(dev):
-        _abi.check(lib.fcsa_forward_fused(_abi.ref(p), _abi.ref(_view4(q, sh.qkind)), _abi.ref(_view4(k, sh.kkind)),
-                                          _abi.ref(_view4(v, sh.kkind)), _abi.ref(n), _abi.ref(_view4(o, sh.qkind)),
-                                          inv_l.data_ptr() if need_inv_l else None, _stream(dev)))
-    return o, inv_l, qn, kn, rq, rk
-
-
-def _attn_backward_fused(do, o, inv_l, qn, kn, v, rq, rk, mask_u8, scale, shift, causal, groups):
-    """gradients w.r.t. the raw q, k and v through fcsa_backward_fused."""
-    lib = _abi.load()
-    sh = _Shapes(qn, kn, v)
-    v, o, do = _tma_ready(v), _tma_ready(o), _tma_ready(do)
-    dev = qn.device
-    dq = torch.empty(qn.shape, dtype=qn.dtype, device=dev)
-    dk = torch.empty(kn.shape, dtype=kn.dtype, device=dev)
-    dv = torch.empty(v.shape, dtype=v.dtype, device=dev)
-    p = _problem(sh, qn.dtype, scale, shift, causal, mask_u8)
-    n = _l2norm_struct(sh, groups, qn, kn, rq, rk)
-    nbytes = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        _abi.check(lib.fcsa_backward_fused(
-            _abi.ref(p), _abi.ref(n), _abi.ref(_view4(v, sh.kkind)), _abi.ref(_view4(o, sh.qkind)),
-            _abi.ref(_view4(do, sh.qkind)), inv_l.data_ptr(), _abi.ref(_view4(dq, sh.qkind)),
-            _abi.ref(_view4(dk, sh.kkind)), _abi.ref(_view4(dv, sh.kkind)), ws.data_ptr(), nbytes, _stream(dev)))
-    return dq, dk, dv
-
-
-def _l2norm_forward(x, groups):
-    """CUDA kernel: x -> (x normalised per group, 1/norm) with x 3-D or 4-D."""
-    lib = _abi.load()
-    x = _tma_ready(x)
-    kind = "bhnd" if x.ndim == 4 else "bnd"
-    B = x.shape[0]
-    H = x.shape[1] if x.ndim == 4 else 1
-    N, D = x.shape[-2], x.shape[-1]
-    y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
-    rnorm = torch.empty((B, H, N, groups), dtype=torch.float32, device=x.device)
-    tx, ty = _view4(x, kind), _view4(y, kind)
-    with torch.cuda.device(x.device):
-        _abi.check(lib.fcsa_l2norm_forward(_KERNEL_DTYPES[x.dtype], B, H, N, D, groups, _abi.ref(tx),
-                                           _abi.ref(ty), rnorm.data_ptr(), _stream(x.device)))
-    return y, rnorm
-
-
-def _l2norm_backward(dy, y, rnorm, groups):
-    lib = _abi.load()
-    dy, y = _tma_ready(dy), _tma_ready(y)
-    kind = "bhnd" if y.ndim == 4 else "bnd"
-    B = y.shape[0]
-    H = y.shape[1] if y.ndim == 4 else 1
-    N, D = y.shape[-2], y.shape[-1]
-    dx = torch.empty(y.shape, dtype=y.dtype, device=y.device)
-    with torch.cuda.device(y.device):
-        _abi.check(lib.fcsa_l2norm_backward(_KERNEL_DTYPES[y.dtype], B, H, N, D, groups,
-                                            _abi.ref(_view4(dy, kind)), _abi.ref(_view4(y, kind)),
-                                            rnorm.data_ptr(), _abi.ref(_view4(dx, kind)), _stream(y.device)))
-    return dx
+        raise ImportError(
+            f"{name} (the torch extension module over libfcsa_b200.so) is not built in {here}: run "
+            "`python -m flash_cosine_sim_attention_b200.build` (needs nvcc and g++; sm_100a only).  "
+            "There is no CPU fallback.")
+    _abi.load()                                  # fail with the library's own message if the .so is missing
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules[name] = mod
+    _ext_module = mod
+    return mod
 
 
 # --------------------------------------------------------------------------------------------
@@ -304,53 +145,68 @@ def forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift=
     """Same contract as the reference's pybind `forward`: returns (o, inv_l, should_backwards).
     `shift` (extra, optional): the constant subtracted from the logits; the reference's is `scale`."""
     assert not (causal and exists(mask)), "mask should not be supplied if causality is needed"
-    sh = _Shapes(q, k, v)
-    if sh.merged:
-        attn_bias_batch_dim = True          # reference cu:1647-1654
+    ext = _ext()
+    if shift is None:
+        return ext.forward(q, k, v, mask, attn_bias, bool(attn_bias_batch_dim), float(scale), bool(causal))
     should_backwards = any(t.requires_grad for t in (q, k, v)) or (exists(attn_bias) and attn_bias.requires_grad)
-    o, inv_l = _attn_forward(q, k, v, _prep_mask(mask, sh), scale, scale if shift is None else shift, causal,
-                             need_inv_l=True, bias=attn_bias, bias_batch_dim=attn_bias_batch_dim)
+    bias = ext.prepare_bias(q, k, v, attn_bias, bool(attn_bias_batch_dim)) if exists(attn_bias) else None
+    o, inv_l = ext.forward_ex(q, k, v, mask, bias, bool(attn_bias_batch_dim) or q.ndim == 3, None, float(scale),
+                              float(shift), bool(causal), 0, True)[:2]
     return o, inv_l, should_backwards
 
 
 def backward(d_out, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift=None):
     """Same contract as the reference's pybind `backward`: returns (dq, dk, dv, db)."""
-    sh = _Shapes(q, k, v)
-    sft = scale if shift is None else shift
-    if not exists(attn_bias):
-        dq, dk, dv = _attn_backward(d_out, o, inv_l, q, k, v, _prep_mask(mask, sh), scale, sft, causal)
-        return dq, dk, dv, None
-    if sh.merged:
-        attn_bias_batch_dim = True
-    return _attn_backward(d_out, o, inv_l, q, k, v, _prep_mask(mask, sh), scale, sft, causal, bias=attn_bias,
-                          bias_batch_dim=attn_bias_batch_dim, bias_grad=attn_bias.requires_grad)
+    ext = _ext()
+    if shift is None:
+        return ext.backward(d_out, o, inv_l, q, k, v, mask, attn_bias, bool(attn_bias_batch_dim), float(scale),
+                            bool(causal))
+    bias = ext.prepare_bias(q, k, v, attn_bias, bool(attn_bias_batch_dim)) if exists(attn_bias) else None
+    dq, dk, dv, db = ext.backward_ex(d_out, o, inv_l, q, k, v, None, None, mask, bias,
+                                     bool(attn_bias_batch_dim) or q.ndim == 3, None,
+                                     exists(attn_bias) and attn_bias.requires_grad, attn_bias, float(scale),
+                                     float(shift), bool(causal), 0)
+    return dq, dk, dv, db
 
 
 def debug():
     """Reference: a no-op hook (cu:1921).  Here: number of kernels launched by the library."""
-    return int(_abi.load().fcsa_debug())
+    return int(_ext().debug())
 
 
 class FlashCosineSimAttention(Function):
-    """The reference's autograd.Function (py:245-304) on already-normalised q, k."""
+    """The reference's autograd.Function (py:245-304) on already-normalised q, k.  Extra optional
+    arguments: `shift` (constant subtracted from the logits, default = scale as in the reference) and
+    `bias_amax` (fp32 device scalar >= the bias values; added to the shift inside the kernels)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim, shift=None):
-        o, inv_l, should_backwards = forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift)
+    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim, shift=None, bias_amax=None):
+        assert not (causal and exists(mask)), "mask should not be supplied if causality is needed"
+        ext = _ext()
+        batch_dim = bool(attn_bias_batch_dim) or q.ndim == 3          # reference cu:1647-1654
+        should_backwards = any(t.requires_grad for t in (q, k, v)) or (exists(attn_bias) and attn_bias.requires_grad)
+        bias = ext.prepare_bias(q, k, v, attn_bias, batch_dim) if exists(attn_bias) else None
+        sft = float(scale if shift is None else shift)
+        o, inv_l = ext.forward_ex(q, k, v, mask, bias, batch_dim, bias_amax, float(scale), sft, bool(causal), 0,
+                                  should_backwards)[:2]
         if not should_backwards:
             return o
         ctx.should_backwards = should_backwards
-        ctx.save_for_backward(o, inv_l, q, k, v, mask, attn_bias)
-        ctx.params = (scale, causal, attn_bias_batch_dim, shift)
+        # the padded / aligned bias is saved, not rebuilt in the backward
+        ctx.save_for_backward(o, inv_l, q, k, v, mask, bias, bias_amax)
+        ctx.params = (float(scale), bool(causal), batch_dim, sft,
+                      exists(attn_bias) and attn_bias.requires_grad, attn_bias.dtype if exists(attn_bias) else None)
         return o
 
     @staticmethod
     def backward(ctx, do):
         assert ctx.should_backwards
-        o, inv_l, q, k, v, mask, attn_bias = ctx.saved_tensors
-        scale, causal, attn_bias_batch_dim, shift = ctx.params
-        dq, dk, dv, db = backward(do, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift)
-        return dq, dk, dv, None, db, None, None, None, None
+        o, inv_l, q, k, v, mask, bias, bias_amax = ctx.saved_tensors
+        scale, causal, batch_dim, shift, bias_grad, bias_dtype = ctx.params
+        like = torch.empty(0, dtype=bias_dtype, device=q.device) if bias_grad else None
+        dq, dk, dv, db = _ext().backward_ex(do, o, inv_l, q, k, v, None, None, mask, bias, batch_dim, bias_amax,
+                                            bias_grad, like, scale, shift, causal, 0)
+        return dq, dk, dv, None, db, None, None, None, None, None
 
 
 flash_cosine_sim_attention_cuda = FlashCosineSimAttention.apply
@@ -379,31 +235,26 @@ class _FusedCosineSimAttention(Function):
 
     @staticmethod
     def forward(ctx, q, k, v, mask, scale, causal, groups, l2norm_qk, shift_groups=0):
-        sh = _Shapes(q, k, v)
-        mask_u8 = _prep_mask(mask, sh)
+        ext = _ext()
         # shift_groups > 0: q, k arrive already normalised over that many groups (padded head dims)
         shift = (_choose_shift(q.dtype, scale, shift_groups, True) if shift_groups > 0
                  else _choose_shift(q.dtype, scale, groups, l2norm_qk))
         needs_grad = any(ctx.needs_input_grad[:3])
-        if l2norm_qk:
-            o, inv_l, qn, kn, rq, rk = _attn_forward_fused(q, k, v, mask_u8, scale, shift, causal, groups,
-                                                           need_inv_l=needs_grad)
-        else:
-            qn, kn, rq, rk = q, k, None, None
-            o, inv_l = _attn_forward(qn, kn, v, mask_u8, scale, shift, causal, need_inv_l=needs_grad)
+        o, inv_l, qn, kn, rq, rk = ext.forward_ex(q, k, v, mask, None, False, None, scale, shift, causal,
+                                                  groups if l2norm_qk else 0, needs_grad)
         if needs_grad:
-            ctx.save_for_backward(o, inv_l, qn, kn, v, mask_u8, rq, rk)
+            if not l2norm_qk:
+                qn, kn = q, k
+            ctx.save_for_backward(o, inv_l, qn, kn, v, mask, rq, rk)
             ctx.params = (scale, shift, causal, groups, l2norm_qk)
         return o
 
     @staticmethod
     def backward(ctx, do):
-        o, inv_l, qn, kn, v, mask_u8, rq, rk = ctx.saved_tensors
+        o, inv_l, qn, kn, v, mask, rq, rk = ctx.saved_tensors
         scale, shift, causal, groups, l2norm_qk = ctx.params
-        if l2norm_qk:
-            dq, dk, dv = _attn_backward_fused(do, o, inv_l, qn, kn, v, rq, rk, mask_u8, scale, shift, causal, groups)
-        else:
-            dq, dk, dv = _attn_backward(do, o, inv_l, qn, kn, v, mask_u8, scale, shift, causal)
+        dq, dk, dv, _ = _ext().backward_ex(do, o, inv_l, qn, kn, v, rq, rk, mask, None, False, None, False, None,
+                                           scale, shift, causal, groups if l2norm_qk else 0)
         return dq, dk, dv, None, None, None, None, None, None
 
 
@@ -412,7 +263,7 @@ class _L2Norm(Function):
 
     @staticmethod
     def forward(ctx, x, groups):
-        y, rnorm = _l2norm_forward(x, groups)
+        y, rnorm = _ext().l2norm_forward(x, groups)
         ctx.save_for_backward(y, rnorm)
         ctx.groups = groups
         return y
@@ -420,7 +271,7 @@ class _L2Norm(Function):
     @staticmethod
     def backward(ctx, dy):
         y, rnorm = ctx.saved_tensors
-        return _l2norm_backward(dy, y, rnorm, ctx.groups), None
+        return _ext().l2norm_backward(dy, y, rnorm, ctx.groups), None
 
 
 # --------------------------------------------------------------------------------------------
@@ -523,12 +374,14 @@ def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
         # attention kernels; d_bias is reduced in fp32 and returned in the bias's dtype
         if l2norm_qk:
             q, k = l2norm_tensors(q, k, groups=groups)
-        shift = _choose_shift(q.dtype, scale, groups if l2norm_qk else 1, True)
-        if q.dtype == torch.float16:
-            # p = exp(logit - shift) is stored in fp16: keep its top below 2^15 whatever the bias adds
-            shift += max(float(attn_bias.detach().amax()), 0.0)
+        shift = _choose_shift(q.dtype, scale, groups if l2norm_qk else 1, l2norm_qk)
+        amax = None
+        if q.dtype == torch.float16 and l2norm_qk:
+            # p = exp(logit - shift) is stored in fp16: keep its top below 2^15 whatever the bias adds.  The
+            # bound stays on the device (a 1-element tensor the kernels read) - no host synchronisation.
+            amax = attn_bias.detach().amax().float().reshape(1)
         return FlashCosineSimAttention.apply(q, k, v, mask, attn_bias, float(scale), bool(causal),
-                                             bool(attn_bias_batch_dim), float(shift))
+                                             bool(attn_bias_batch_dim), float(shift), amax)
     if not _kernel_supported(q, k, v, attn_bias):
         # float32 inputs and head dims above 128 / not a multiple of 8 have no sm_100a kernel yet:
         # they run the un-fused formulation on the same GPU (correct, slower), never silently wrong.

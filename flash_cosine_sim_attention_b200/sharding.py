@@ -71,14 +71,31 @@ class _SharedAcrossRanks(Function):
         return g, None
 
 
-def sharded_flash_cosine_sim_attention(q, k, v, mask=None, *, gather=False, group=None, attn_fn=None, **kwargs):
+def local_shard(t, rank, world, dim=0):
+    """This rank's contiguous slice of `t` along `dim` (the batch dimension by default): what a
+    data-parallel rank holds when the global batch is split over the ranks."""
+    lo, hi = shard_range(t.shape[dim], rank, world)
+    return t.narrow(dim, lo, hi - lo)
+
+
+def sharded_flash_cosine_sim_attention(q, k, v, mask=None, *, gather=False, group=None, attn_fn=None,
+                                       presharded=False, **kwargs):
     """Run this rank's (batch x heads) shard of the attention; q, k, v, mask are the FULL tensors
     (identical on every rank).  Returns the local output shard, or the full output if gather=True.
+
+    presharded=True: q, k, v, mask are ALREADY this rank's batch shard (the usual data-parallel
+    situation: every rank owns its batch elements, equal counts per rank) - nothing is sliced, gradients
+    have the shard's size, and the only possible collective is the optional all-gather of `o`.
 
     attn_fn defaults to the fused CUDA operator; the CPU tests pass plain_cosine_sim_attention."""
     attn_fn = attn_fn or flash_cosine_sim_attention
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if presharded:
+        o = attn_fn(q, k, v, mask=mask, **kwargs)
+        if gather and world > 1:
+            o = _AllGather.apply(o, 0, [q.shape[0]] * world, rank, group)
+        return o
     if q.ndim == 3 or world == 1:
         dim, total = 0, q.shape[0]                      # merged batch-heads: plain batch split
         kind = "batch"

@@ -93,19 +93,33 @@ int64_t fcsa_debug(void);
 int fcsa_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
                  const fcsa_tensor* v, const fcsa_tensor* o, float* inv_l, void* stream);
 
-/* Bytes of scratch fcsa_backward needs for this problem (fp32 dq / shared-kv accumulators, delta). */
+/* Bytes of SCRATCH fcsa_backward needs for this problem (per-row constants, shared-kv accumulators):
+ * contents irrelevant on entry, garbage on exit. */
 size_t fcsa_backward_workspace_bytes(const fcsa_problem* p);
+
+/* Bytes of the ZEROED workspace of fcsa_backward (fp32 dq accumulator tiles + per-tile arrival counters).
+ * Contract: every byte is zero when a backward call starts and zero again when its kernels have
+ * finished - whoever converts an accumulator tile to dq also clears it - so one buffer, zero-filled
+ * ONCE (fcsa_zeroed_init), serves any number of calls of any shape enqueued on the same stream.
+ * This is what replaces the reference's per-call 33.5 MB memset of its fp32 dq (cu:1818) and its
+ * separate cast pass (cu:1904).  Do not share one buffer between streams that may run concurrently. */
+size_t fcsa_backward_zeroed_bytes(const fcsa_problem* p);
+
+/* Zero-fill a freshly allocated (or grown) zeroed workspace: cudaMemsetAsync on `stream`. */
+int fcsa_zeroed_init(void* zeroed, size_t bytes, void* stream);
 
 /*
  * Gradients of fcsa_forward w.r.t. q, k, v (the q, k given are the already-normalised ones,
  * exactly as in the reference: cu:1487-1626).  dq/dk/dv are caller-allocated in the problem
  * dtype; with kv_heads == 1, dk/dv have a single head and receive the sum over heads
- * (cu:1613-1619).  `workspace` must hold fcsa_backward_workspace_bytes(p) bytes.
+ * (cu:1613-1619).  `workspace` must hold fcsa_backward_workspace_bytes(p) bytes, `zeroed`
+ * fcsa_backward_zeroed_bytes(p) bytes that are all zero (see above).
  */
 int fcsa_backward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor* k,
                   const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
                   const float* inv_l, const fcsa_tensor* dq, const fcsa_tensor* dk,
-                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* stream);
+                  const fcsa_tensor* dv, void* workspace, size_t workspace_bytes, void* zeroed,
+                  size_t zeroed_bytes, void* stream);
 
 /*
  * y = x / max(||x||_2, 1e-12) over `groups` equal chunks of the feature dimension
@@ -148,11 +162,12 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
                        void* stream);
 
 /* Gradients w.r.t. the RAW q, k (and v): fcsa_backward followed by the l2norm backward, the latter
- * folded into the dq finish pass and the dk epilogue.  Same workspace as fcsa_backward. */
+ * folded into the dq conversion and the dk epilogue.  Same workspaces as fcsa_backward. */
 int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_tensor* v,
                         const fcsa_tensor* o, const fcsa_tensor* d_o, const float* inv_l,
                         const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        void* workspace, size_t workspace_bytes, void* zeroed, size_t zeroed_bytes,
+                        void* stream);
 
 /* ---- additive attention bias -------------------------------------------------------------------
  * Replaces the `attn_bias` / `attn_bias_batch_dim` arguments of the reference's forward / backward
@@ -164,6 +179,11 @@ int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_
 typedef struct fcsa_bias {
   const void* ptr;
   int64_t sb, sh, sn;
+  /* Optional DEVICE pointer to one fp32: an upper bound of the bias values (e.g. its max).  The kernels
+   * add max(*amax, 0) to the problem's `shift`, which keeps p = exp(logit - shift) inside the fp16 range
+   * whatever the bias adds - without the host ever reading the bias (no device synchronisation).
+   * Pass the same pointer to the forward and the backward; NULL = use `shift` as is. */
+  const float* amax;
 } fcsa_bias;
 
 /* fcsa_forward with the bias added to scale * q.k before the exponential. */
@@ -179,7 +199,8 @@ int fcsa_backward_bias(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
                        const fcsa_tensor* v, const fcsa_tensor* o, const fcsa_tensor* d_o,
                        const float* inv_l, const fcsa_bias* bias, float* d_bias_acc, int64_t dsb,
                        int64_t dsh, const fcsa_tensor* dq, const fcsa_tensor* dk, const fcsa_tensor* dv,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       void* workspace, size_t workspace_bytes, void* zeroed, size_t zeroed_bytes,
+                       void* stream);
 
 /*
  * Measurement hook (bench.py roofline line; no reference counterpart - the reference only timed

@@ -12,6 +12,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not errored) on a box without a CUDA device, so a plain
+    `pytest tests` works on CPU-only CI.  On a GPU box nothing is skipped here: a missing native
+    library must FAIL there (the product has no fallback), which the tests' own fixtures check."""
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:       # noqa: BLE001
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200): run with -m gpu on the GPU box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")

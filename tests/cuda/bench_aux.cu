@@ -1,4 +1,4 @@
-// Times the HBM-bound helper kernels (l2norm pair, backward preprocess, dq finish) at the benchmark
+// Times the HBM-bound helper kernels (l2norm pair, backward preprocess) at the benchmark
 // shape with an L2 flush between repetitions.  Test infrastructure only.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o bench_aux bench_aux.cu
 #include <stdio.h>
@@ -50,24 +50,18 @@ int main() {
     dim3 grid(148 * 4);
     time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 4><<<grid, 256>>>(pa); }, 4.0 * n * 2);
   }
-  // prep
+  // prep (per-row constants + slivers; no accumulator zeroing any more)
   {
-    fcsa::PrepArgs p; p.aug = nullptr; p.ones = nullptr; p.inv_c1 = 1.f; p.B = B; p.H = H; p.Nq = N; p.D = D; p.nqt = w.nqt; p.QT = w.QT; p.c2 = 11.5f;
+    fcsa::PrepArgs p; memset(&p, 0, sizeof(p));
+    p.aug = (char*)ws + w.aug_off; p.ones = (char*)ws + w.ones_off; p.inv_c1 = 1.f; p.B = B; p.H = H; p.Nq = N; p.Nk = N; p.D = D;
+    p.nqt = w.nqt; p.QT = w.QT; p.c2 = 11.5f; p.causal = 1; p.shift_extra = nullptr;
     p.o = o; p.o_sb = sb; p.o_sh = sh; p.o_sn = sn; p.d_o = d_o; p.do_sb = sb; p.do_sh = sh; p.do_sn = sn;
-    p.inv_l = inv_l; p.stats = (float*)((char*)ws + w.stats_off); p.dq_acc = (float*)((char*)ws + w.dq_off);
-    const int rows_per_block = 256 / (D / 8);
-    dim3 grid((w.nqt * w.QT + rows_per_block - 1) / rows_per_block, B * H);
-    time_it("bwd_prep (+zero dq_acc)", [&] { fcsa::bwd_prep_kernel<bf16><<<grid, 256>>>(p); }, 2.0 * n * 2 + n * 4.0);
-  }
-  // finish
-  {
-    fcsa::DqFinishArgs f; f.B = B; f.H = H; f.Nq = N; f.D = D; f.nqt = w.nqt; f.scale = 8.f;
-    f.dq_acc = (float*)((char*)ws + w.dq_off); f.dq = dq; f.sb = sb; f.sh = sh; f.sn = sn;
-    f.q_hat = qn; f.q_sb = sb; f.q_sh = sh; f.q_sn = sn; f.q_rnorm = rq; f.G = G;
-    dim3 grid(w.nqt, B * H);
-    time_it("bwd_dq_finish64 (+l2 bwd)", [&] { fcsa::bwd_dq_finish64_kernel<bf16><<<grid, 256>>>(f); }, n * 4.0 + 2.0 * n * 2);
-    f.q_rnorm = nullptr;
-    time_it("bwd_dq_finish64 (plain)", [&] { fcsa::bwd_dq_finish64_kernel<bf16><<<grid, 256>>>(f); }, n * 4.0 + n * 2.0);
+    p.inv_l = inv_l; p.stats = (float*)((char*)ws + w.stats_off);
+    p.dq = dq; p.dq_sb = sb; p.dq_sh = sh; p.dq_sn = sn;
+    const int rows_per_block = 2 * (256 / (D / 8));
+    p.bpb = (w.nqt * w.QT + rows_per_block - 1) / rows_per_block;
+    dim3 grid(p.bpb * B * H);
+    time_it("bwd_prep (delta, slivers)", [&] { fcsa::bwd_prep_kernel<bf16><<<grid, 256>>>(p); }, 2.0 * n * 2 + (double)B * H * N * 64);
   }
   // reference points: plain copies of the same sizes
   time_it("cudaMemcpy D2D 33.5 MB", [&] { CK(cudaMemcpyAsync(qn, q, n * 2, cudaMemcpyDeviceToDevice)); CK(cudaMemcpyAsync(kn, k, n * 2, cudaMemcpyDeviceToDevice)); }, 4.0 * n * 2);

@@ -43,12 +43,16 @@ int main(int argc, char** argv) {
   size_t wsb = fcsa::bwd_workspace_bytes(B, H, H, Nq, Nk, D);
   void* ws;
   CK(cudaMalloc(&ws, wsb));
+  size_t zsb = fcsa::bwd_zeroed_workspace_bytes(B, H, H, Nq, Nk, D);
+  void* zs;
+  CK(cudaMalloc(&zs, zsb));
+  CK(cudaMemset(zs, 0, zsb));
   fcsa::BwdHostArgs h;
   h.dtype_bf16 = true; h.B = B; h.H = H; h.kv_heads = H; h.Nq = Nq; h.Nk = Nk; h.D = D; h.causal = causal;
   h.scale = 8.f; h.shift = 8.f; h.mask = nullptr; h.mask_sb = 0;
   auto T = [&](void* p) { fcsa_tensor t; t.ptr = p; t.sb = (long long)H * N * D; t.sh = (long long)N * D; t.sn = D; return t; };
   h.q = T(q); h.k = T(k); h.v = T(v); h.o = T(o); h.d_o = T(d_o); h.dq = T(dq); h.dk = T(dk); h.dv = T(dv);
-  h.inv_l = inv_l; h.workspace = ws;
+  h.inv_l = inv_l; h.workspace = ws; h.zeroed = zs;
   int launches = 0; const char* err = nullptr; cudaError_t ce = cudaSuccess;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));

@@ -83,7 +83,21 @@ def test_workspace_size_formula(lib):
     n = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
     stats = 4 * 8 * 32 * 256 * 4
     dq = 4 * 8 * 4096 * 64 * 4
+    cnt = 4 * 8 * 32 * 4                    # one arrival counter per 128-row query tile
     aug = 4 * 8 * 4096 * 32 * 2 + 4096      # 16-bit slivers of the augmented contraction + the ones tile
-    assert n == stats + dq + aug
+    assert n == stats + aug                 # scratch: per-row constants only
+    assert lib.fcsa_backward_zeroed_bytes(_abi.ref(p)) == dq + cnt      # self-cleaning: dq accumulator + counters
     p.kv_heads = 1
-    assert lib.fcsa_backward_workspace_bytes(_abi.ref(p)) == stats + dq + aug + 2 * 4 * 4096 * 64 * 4
+    assert lib.fcsa_backward_workspace_bytes(_abi.ref(p)) == stats + aug + 2 * 4 * 4096 * 64 * 4
+    assert lib.fcsa_backward_zeroed_bytes(_abi.ref(p)) == dq + cnt
+
+
+def test_backward_rejects_missing_zeroed_workspace(lib):
+    p = _abi.FcsaProblem()
+    p.dtype, p.batch, p.heads, p.kv_heads, p.seq_q, p.seq_k, p.head_dim = _abi.FCSA_BF16, 1, 1, 1, 128, 128, 64
+    p.scale, p.shift = 8.0, 8.0
+    t = _abi.FcsaTensor(4096, 128 * 64, 128 * 64, 64)
+    need = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
+    rc = lib.fcsa_backward(_abi.ref(p), *([_abi.ref(t)] * 5), 4096, *([_abi.ref(t)] * 3), 4096, need, None, 0, None)
+    assert rc == _abi.FCSA_ERR_WORKSPACE and b"zeroed workspace" in lib.fcsa_last_error()
+    assert lib.fcsa_zeroed_init(None, 0, None) == _abi.FCSA_ERR_INVALID
