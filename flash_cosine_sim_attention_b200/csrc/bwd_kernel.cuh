@@ -696,6 +696,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t progress = sStats;
       uint32_t* const won = reinterpret_cast<uint32_t*>(smem + Cfg::kOffStats + Cfg::kProgressBytes);
       int next = 0;
+#ifdef FCSA_EXP_NO_TICKET
+      next = NI;
+#endif
       while (next < NI) {
         int done = 0x7FFFFFFF;
         if (lane < 16) done = (int)ld_acquire_cta_shared(progress + 4 * lane);
@@ -788,9 +791,14 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if constexpr (FUSE_FINISH) {
           // the reduce of tile j-1 (issued one tile period ago) has fully landed: this warp's share of
           // that tile is done
-          if (j > 0) {
-            bulk_wait_group<1>();
-            st_release_cta_shared(sStats + 4 * warp, (uint32_t)j);     // tiles [0, j) done by this warp
+#ifndef FCSA_EXP_LAG
+#define FCSA_EXP_LAG 1
+#endif
+          if (j >= FCSA_EXP_LAG) {
+#ifndef FCSA_EXP_NO_FULLWAIT
+            bulk_wait_group<FCSA_EXP_LAG>();
+#endif
+            st_release_cta_shared(sStats + 4 * warp, (uint32_t)(j + 1 - FCSA_EXP_LAG));     // tiles [0, j+1-LAG) done by this warp
           }
         }
       }
@@ -989,6 +997,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t* won = reinterpret_cast<const uint32_t*>(smem + Cfg::kOffStats + Cfg::kProgressBytes);
         const int frow = warp * 8 + (lane >> 2);     // row inside the tile
         const int fp = lane & 3;                     // which 16 of the 64 features
+#ifdef FCSA_EXP_NO_FINISH
+        if (false)
+#endif
         for (int w0 = 0; w0 < NI; w0 += 32) {
           uint32_t bits = won[w0 >> 5];
           while (bits) {
