@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -252,7 +252,7 @@ def main():
     barrier()
 
     # ---- device-resident timing -------------------------------------------------------------
-    NEV = 4                                      # l2norm(q,k), forward, preprocess, backward: the kernels of a step
+    NEV = 5                                      # l2norm(q,k), forward, preprocess, backward, dq conversion
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * NEV)] for _ in range(K)]
     for row in kev:                                                                       # materialise handles
@@ -282,7 +282,7 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     # pass 2 - attribution: the same K steps again with events recorded around each kernel of the step
     # (library hook); not part of `value`
-    which = {"l2norm_qk": 2, "forward": 0, "preprocess": 3, "backward": 1}
+    which = {"l2norm_qk": 2, "forward": 0, "preprocess": 3, "backward": 1, "dq_finish": 4}
     with (sampler.window() if sampler else contextlib.nullcontext()):
         torch.cuda._sleep(2_000_000)
         for i in range(K):
@@ -293,6 +293,9 @@ def main():
         barrier()
     for w in range(5):
         lib.fcsa_set_kernel_events(w, None, None)
+    # the poller stops here: NVML queries during the end-to-end pass below were seen to stall the PCIe copies
+    # (30 ms per step instead of 1.5 ms with a 20 ms poll period)
+    clocks = sampler.stop() if sampler else None
     parts = {name: sum(r[2 * slot].elapsed_time(r[2 * slot + 1]) for r in kev) / K for slot, name in enumerate(which)}
     fwd_avg, bwd_avg = parts["forward"], parts["backward"]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -340,7 +343,7 @@ def main():
     e2e_run(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with (sampler.window() if sampler else contextlib.nullcontext()):
+    with contextlib.nullcontext():
         e0.record()
         for st in (s_up, s_cmp, s_dn):
             st.wait_stream(torch.cuda.current_stream())
@@ -424,7 +427,6 @@ def main():
     total_ms, e2e_ms = float(total_ms.item()), float(e2e_ms.item())
 
     if rank == 0:
-        clocks = sampler.stop()
         peaks = load_peaks()
         value = STEP_FLOPS * K * world / (total_ms * 1e-3) / 1e12
         e2e_val = STEP_FLOPS * K * world / (e2e_ms * 1e-3) / 1e12
@@ -433,7 +435,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("fcsa_bwd_kernel_dram_bytes_per_launch")
-        aux = parts["l2norm_qk"] + parts["preprocess"]
+        aux = parts["l2norm_qk"] + parts["preprocess"] + parts["dq_finish"]
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,7 +449,7 @@ def main():
                                  "each between its own CUDA events, barrier+sync; max over ranks",
                        "flops_per_step_per_gpu": STEP_FLOPS},
             "frac_of_peak": value / world / peaks["bf16"], "peak_source": peaks["source"],
-            "roofline": {"bound": "tensor", "kernel": "fcsa_bwd_kernel<bf16,64> (incl. the fused dq conversion)",
+            "roofline": {"bound": "tensor", "kernel": "fcsa_bwd_kernel<bf16,64>",
                          "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": ach / peaks["bf16"],
                          "traffic": traffic, "ms": bwd_avg, "flops_per_launch": BWD_FLOPS},
             "roofline_fwd": {"bound": "tensor", "kernel": "fcsa_fwd_kernel<bf16,64>",
@@ -458,8 +460,7 @@ def main():
                     "d2h_bytes_per_step": 4 * B * H * N * D * 2 * world, "ms_per_step": e2e_ms / K},
             "step_breakdown_ms": {**parts, "aux_total": aux,
                                   "note": "instrumented second pass (events between the launches); the headline pass "
-                                          "has none.  The dq conversion (a separate 29 us pass in round 1) now runs "
-                                          "inside the backward kernel"},
+                                          "has none"},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
             "host_enqueue_us_per_step": host_enqueue_us, "clocks": clocks,
             "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],

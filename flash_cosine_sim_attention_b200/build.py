@@ -75,7 +75,9 @@ def ext_compile_command(out=None):
     cmd += [EXT_SRC, "-o", out or ext_path()]
     cmd += [f"-L{d}" for d in libdirs] + [f"-L{HERE}", "-l:libfcsa_b200.so"]
     cmd += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
-    cmd += ["-Wl,-rpath,$ORIGIN"] + [f"-Wl,-rpath,{d}" for d in ce.library_paths()]
+    # $ORIGIN: in-tree (module next to the library); $ORIGIN/<package>: pip-installed (module top-level)
+    cmd += ["-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/flash_cosine_sim_attention_b200"]
+    cmd += [f"-Wl,-rpath,{d}" for d in ce.library_paths()]
     return cmd
 
 

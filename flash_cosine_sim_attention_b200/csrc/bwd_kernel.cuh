@@ -74,15 +74,6 @@ struct BwdCfg {
   //   aug S  : QT queries x 16, columns 0..2 = c3/c1 split in three 16-bit parts   (B operand)
   //   aug dP : QT queries x 16, columns 0..2 = -delta split in three 16-bit parts  (B operand)
   static constexpr bool kAug = (D == 64);
-  // D = 64: the dq finish pass runs inside the main kernel ("last CTA of a query tile converts it"); the
-  // list of tiles a CTA has to convert is a bitmap in the (otherwise unused) stats stages: 3 KB = 24576 tiles
-#ifdef FCSA_EXP_SKIP_REDUCE
-  static constexpr bool kFuseFinish = false;
-#else
-  static constexpr bool kFuseFinish = (D == 64);
-#endif
-  static constexpr int kProgressBytes = 64;               // 16 per-warp "tiles reduced" counters
-  static constexpr int kMaxFusedTiles = (3 * 1024 - kProgressBytes) * 8;
   static constexpr int kSliver = QT * 32;                 // bytes of one QT x 16 sliver
   static constexpr int kOffOnes = kOffStats + NST * 1024;
   static constexpr int kOffAug = kOffOnes + (kAug ? 4096 : 0);        // NST stages x {aug S, aug dP}
@@ -104,18 +95,16 @@ struct BwdCfg {
 //   aug   : 16-bit [B*H][nqt*QT][32]  cols 0..2 = c3/c1 in three parts, cols 16..18 = -delta in three
 //           parts, rest 0 (the extra K = 16 step of S^T and dP^T, D = 64); ones: 16-bit [128][16]
 //
-// ZEROED workspace (all zero on entry - the caller zero-fills it ONCE, fcsa_workspace_init - and all
-// zero again on exit: whoever converts an accumulator tile also clears it, so no per-call memset /
-// zeroing pass is needed; reference: a 33.5 MB cudaMemset of dq per backward, cu:1818):
+// ZEROED workspace (all zero on entry - the caller zero-fills it ONCE, fcsa_zeroed_init - and all
+// zero again on exit: the dq conversion pass clears every accumulator tile it converts, so no per-call
+// memset / zeroing pass is needed; reference: a 33.5 MB cudaMemset of dq per backward, cu:1818):
 //   dq_acc: fp32 [B*H][nqt][4 warps][16 chunks][32 lanes][4]   32 KB per query tile, in the order the
 //           reduce warps produce it (D = 64: lane = query row, chunk = 4 features;
 //           D = 128: lane = feature, chunk = 4 query rows)
-//   cnt   : int32 [B*H][nqt]  arrivals per query tile (D = 64: the CTA that makes the count complete
-//           converts the tile inside the main kernel)
 // ------------------------------------------------------------------------------------------
 struct BwdWorkspace {
   size_t stats_off, dkv_off, aug_off, ones_off, total;     // scratch
-  size_t dq_off, cnt_off, ztotal;                           // zeroed
+  size_t dq_off, ztotal;                                    // zeroed
   int nqt, QT;
 };
 
@@ -125,7 +114,6 @@ inline BwdWorkspace bwd_workspace_layout(int B, int H, int kv_heads, int Nq, int
   w.nqt = (Nq + w.QT - 1) / w.QT;
   size_t stats = (size_t)B * H * w.nqt * 2 * w.QT * 4;
   size_t dq = (size_t)B * H * w.nqt * 32768;
-  size_t cnt = (size_t)B * H * w.nqt * 4;
   size_t dkv = (kv_heads == 1 && H > 1) ? (size_t)2 * B * Nk * D * 4 : 0;
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   // augmented-contraction operands (16-bit): [B*H][nqt*QT][32] and the 128 x 16 ones tile
@@ -136,8 +124,7 @@ inline BwdWorkspace bwd_workspace_layout(int B, int H, int kv_heads, int Nq, int
   w.ones_off = w.aug_off + up(aug);
   w.total = w.ones_off + 4096;
   w.dq_off = 0;
-  w.cnt_off = up(dq);
-  w.ztotal = w.cnt_off + up(cnt);
+  w.ztotal = up(dq);
   return w;
 }
 
@@ -163,9 +150,6 @@ struct PrepArgs {
   void* aug;                        // 16-bit [B*H][nqt*QT][32] (see workspace layout) or nullptr
   void* ones;                       // 16-bit [128][16]
   float inv_c1;                     // 1 / (scale * log2e)
-  // fused dq finish (D = 64): query tiles that no key tile visits (causal with Nq > Nk) get their
-  // dq rows zeroed here, because no CTA of the main kernel will ever convert them
-  void* dq; long long dq_sb, dq_sh, dq_sn;
 };
 
 // x = p0 + p1 + p2 with each part representable in T (16 bit): 24 bits of x survive
@@ -177,16 +161,6 @@ __device__ __forceinline__ void split3(float x, uint32_t& w01, uint32_t& w2) {
   const float e2 = e1 - r1.x;
   w01 = pack2<T>(r0.x, r1.x);
   w2 = pack2<T>(e2, 0.f);
-}
-
-// number of key tiles (128 keys) whose CTA visits query tile qt = arrivals the tile's counter must see
-__host__ __device__ __forceinline__ int bwd_tile_contributors(int qt, int QT, int Nq, int Nk, int causal) {
-  const int nkt = (Nk + 127) >> 7;
-  if (!causal) return nkt;
-  const int last = qt * QT + QT - 1 + (Nk - Nq);      // last key column any row of the tile can see
-  if (last < 0) return 0;
-  const int c = (last >> 7) + 1;
-  return c < nkt ? c : nkt;
 }
 
 template <typename T>
@@ -226,9 +200,6 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
     for (int m = 1; m < tpr; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
     if (!in[u]) continue;
     const int qt = row[u] / a.QT, r = row[u] - qt * a.QT;
-    if (a.dq != nullptr && valid[u] && bwd_tile_contributors(qt, a.QT, a.Nq, a.Nk, a.causal) == 0)
-      *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.dq) + b * a.dq_sb + h * a.dq_sh + (long long)row[u] * a.dq_sn +
-                                tr * 8) = make_uint4(0, 0, 0, 0);
     if (tr != 0) continue;
     float* st = a.stats + ((long long)bh * a.nqt + qt) * 2 * a.QT;
     float c3 = 0.f, dl = 0.f;
@@ -279,9 +250,8 @@ struct BwdArgs {
   // index space ([.][.][Nq][Nk] planes, strides dbias_sb (0 = summed over the batch) / dbias_sh) or nullptr.
   const void* bias; long long bias_sb, bias_sh, bias_sn;
   float* dbias; long long dbias_sb, dbias_sh;
-  // fused dq finish (D = 64): the CTA whose arrival completes a query tile's counter converts the fp32
-  // accumulator tile to 16-bit dq (x scale, optional l2norm backward w.r.t. the raw q) and clears it
-  int* cnt;                         // [B*H][nqt] arrivals, zero between launches
+  // dq conversion pass (D = 64, bwd_dq_finish64_kernel): fp32 accumulator tile -> 16-bit dq (x scale,
+  // optional l2norm backward w.r.t. the raw q), tile cleared
   void* dq; long long dq_sb, dq_sh, dq_sn;
   const void* q_hat; long long q_sb, q_sh, q_sn;   // normalised q (only read when q_rnorm is set)
   const float* q_rnorm;             // (B, H, Nq, G) or nullptr
@@ -306,12 +276,13 @@ __device__ __forceinline__ float4 ldg_cg128f(const float* p) {
   return v;
 }
 
-// Fused dq finish, D = 64 (replaces the separate finish pass; reference: the fp32 -> scalar_t cast of dq
-// after its atomics, cu:1904).  Accumulator tile = [4 row quarters][16 feature chunks][32 rows][4 features].
-// Called by every compute warp for the same tile: warp w converts rows [8w, 8w+8) - four adjacent
-// lanes share a row, 16 features each - so that group sums of the l2norm backward
+// dq conversion, D = 64 (reference: the fp32 -> scalar_t cast of dq after its atomics, cu:1904).
+// Accumulator tile = [4 row quarters][16 feature chunks][32 rows][4 features].  One warp converts 8 rows:
+// four adjacent lanes share a row, 16 features each - every 16-byte load of a warp covers whole 128-byte
+// lines, and group sums of the l2norm backward
 //     dq_raw = (dq_hat - q_hat <q_hat, dq_hat>_group) * rnorm_group            (py:38-65 + autograd)
-// are shuffles among those lanes.  The tile is read from L2, converted, and written back as zeros.
+// are shuffles among those lanes.  The tile is read from L2 (the bulk reduce-adds of the main kernel have
+// just produced it there), converted, and written back as zeros: the accumulator is zero between launches.
 template <typename T>
 __device__ __forceinline__ void finish_dq_tile64(const BwdArgs& a, int bh, int b, int h, int qt, int row, int part) {
   float* tile = a.dq_acc + ((long long)bh * a.nqt + qt) * 8192;
@@ -404,7 +375,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                      TM_DQ = Cfg::TM_DQ, TM_X = Cfg::TM_X;
   constexpr bool KV_IN_TMEM = (D == 64);
   constexpr bool AUG = Cfg::kAug;          // per-query constants enter through an extra K = 16 MMA step
-  constexpr bool FUSE_FINISH = Cfg::kFuseFinish;   // dq accumulator tiles are converted in this kernel
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -476,12 +446,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 17) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
-  }
-  if constexpr (FUSE_FINISH) {
-    if (warp == 19) {   // per-warp progress counters + bitmap of the tiles this CTA will convert
-      uint32_t* const z = reinterpret_cast<uint32_t*>(smem + Cfg::kOffStats);
-      for (int wi = lane; wi < Cfg::kProgressBytes / 4 + (NI + 31) / 32; wi += 32) z[wi] = 0u;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -686,49 +650,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_commit(BAR(DKV_FULL));
         }
       }
-    } else if (FUSE_FINISH && warp == 19) {
-      // =============================== tile tickets (fused dq finish) ==============
-      // progress[w] = number of query tiles whose bulk reduce-adds compute warp w has seen COMPLETE
-      // (cp.async.bulk.wait_group, not .read).  When all 16 warps are past tile j this warp draws one
-      // gpu-scope ticket for (CTA, tile j); the CTA that draws the last ticket of a tile owns its
-      // conversion: the tile goes into a bitmap the compute warps walk after their main loop.  No CTA
-      // ever waits for another one, and the compute warps never wait for this warp.
-      const uint32_t progress = sStats;
-      uint32_t* const won = reinterpret_cast<uint32_t*>(smem + Cfg::kOffStats + Cfg::kProgressBytes);
-      int next = 0;
-#ifdef FCSA_EXP_NO_TICKET
-      next = NI;
-#endif
-      while (next < NI) {
-        int done = 0x7FFFFFFF;
-        if (lane < 16) done = (int)ld_acquire_cta_shared(progress + 4 * lane);
-#pragma unroll
-        for (int m = 8; m >= 1; m >>= 1) done = min(done, __shfl_xor_sync(0xFFFFFFFFu, done, m));
-        done = __shfl_sync(0xFFFFFFFFu, done, 0);
-        if (done <= next) {
-          __nanosleep(200);
-          continue;
-        }
-        __syncwarp();
-        const int j = next + lane;
-        bool win = false;
-        if (j < done) {
-          const int qt = i_lo + j;
-          const int expected = bwd_tile_contributors(qt, QT, a.Nq, a.Nk, a.causal);
-          int* c = a.cnt + (long long)bh * a.nqt + qt;
-          __threadfence();                       // the 16 warps' completed reduce-adds happen-before the ticket
-          const int old = atomicAdd(c, 1);
-          win = (old == expected - 1);
-          if (win) {
-            __threadfence();                     // ... and every other CTA's before our reads of the tile
-            *c = 0;                              // nobody else touches this counter again in this launch
-            atomicOr(&won[j >> 5], 1u << (j & 31));
-          }
-        }
-        next = min(done, next + 32);
-      }
-      __syncwarp();
-      named_bar_sync(3, 512 + 32);              // bitmap complete -> compute warps
     }
   } else {
     // =============================== compute warpgroups =============================
@@ -788,19 +709,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float* dst = a.dq_acc + (((long long)bh * a.nqt + (i_lo + j)) * 4 + wq) * 2048 + wg * 512;
         bulk_reduce_add_f32(dst, my_stage, 2048);
         bulk_commit_group();
-        if constexpr (FUSE_FINISH) {
-          // the reduce of tile j-1 (issued one tile period ago) has fully landed: this warp's share of
-          // that tile is done
-#ifndef FCSA_EXP_LAG
-#define FCSA_EXP_LAG 1
-#endif
-          if (j >= FCSA_EXP_LAG) {
-#ifndef FCSA_EXP_NO_FULLWAIT
-            bulk_wait_group<FCSA_EXP_LAG>();
-#endif
-            st_release_cta_shared(sStats + 4 * warp, (uint32_t)(j + 1 - FCSA_EXP_LAG));     // tiles [0, j+1-LAG) done by this warp
-          }
-        }
       }
 #endif
       if (tr_lane) FCSA_TR(3, j, 1);
@@ -976,40 +884,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         fence_proxy_async_smem();
         reduce_dq(NI - 1);
       }
-      if (lane == 0) {
-        bulk_wait_group<0>();
-        if constexpr (FUSE_FINISH) {
-#ifndef FCSA_EXP_SKIP_REDUCE
-          if (NI > 0) st_release_cta_shared(sStats + 4 * warp, (uint32_t)NI);
-#endif
-        }
-      }
+      if (lane == 0) bulk_wait_group<0>();
       __syncwarp();
-    }
-
-    // ---- fused dq finish: convert the query tiles whose last ticket this CTA drew ----------
-    // Every warp converts 8 rows of each such tile on its own (4 adjacent lanes = one row, 16 features
-    // each; group sums of the l2norm backward are shuffles among them), so nothing synchronises here.
-    if constexpr (FUSE_FINISH) {
-#ifndef FCSA_EXP_SKIP_REDUCE
-      if (NI > 0) {
-        named_bar_sync(3, 512 + 32);             // the ticket warp has filled the bitmap
-        const uint32_t* won = reinterpret_cast<const uint32_t*>(smem + Cfg::kOffStats + Cfg::kProgressBytes);
-        const int frow = warp * 8 + (lane >> 2);     // row inside the tile
-        const int fp = lane & 3;                     // which 16 of the 64 features
-#ifdef FCSA_EXP_NO_FINISH
-        if (false)
-#endif
-        for (int w0 = 0; w0 < NI; w0 += 32) {
-          uint32_t bits = won[w0 >> 5];
-          while (bits) {
-            const int j = w0 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            finish_dq_tile64<T>(a, bh, b, h, i_lo + j, frow, fp);
-          }
-        }
-      }
-#endif
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
@@ -1165,10 +1041,23 @@ __device__ __forceinline__ void finish_l2norm_bwd(float (&g)[8], const DqFinishA
   }
 }
 
+// D = 64: one block of 512 threads = one query tile of 128 rows (16 warps x 8 rows).
+template <typename T>
+__global__ void __launch_bounds__(512) bwd_dq_finish64_kernel(const BwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long unit = blockIdx.x;                       // (bh, qt)
+  const int qt = (int)(unit % a.nqt);
+  const int bh = (int)(unit / a.nqt);
+  const int b = bh / a.H, h = bh - b * a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  finish_dq_tile64<T>(a, bh, b, h, qt, warp * 8 + (lane >> 2), lane & 3);
+}
+
 // D = 128: accumulator tile (64 query rows) = [4 warps][16 row-chunks][32 features][4 rows], i.e.
 // transposed.  One block = one tile: coalesced float4 loads -> shared memory -> row-major stores; the
 // tile is written back as zeros (the accumulator is zero between launches, see the workspace layout).
-// (D = 64 converts its tiles inside the main kernel: finish_dq_tile64.)
+
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArgs a) {
   __shared__ float tile[64][129];
@@ -1276,15 +1165,11 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
   uint8_t* zs = reinterpret_cast<uint8_t*>(h.zeroed);
   float* stats = reinterpret_cast<float*>(ws + w.stats_off);
   float* dq_acc = reinterpret_cast<float*>(zs + w.dq_off);
-  int* cnt = reinterpret_cast<int*>(zs + w.cnt_off);
   float* dkv_acc = reinterpret_cast<float*>(ws + w.dkv_off);
   const bool shared_kv = (h.kv_heads == 1 && h.H > 1);
   const float log2e = 1.4426950408889634f;
   cudaError_t e;
-  if (Cfg::kFuseFinish && w.nqt > Cfg::kMaxFusedTiles) {
-    *err = "seq_q too long for the fused dq finish (more than 24064 query tiles)";
-    return FCSA_ERR_UNSUPPORTED;
-  }
+  BwdArgs main_args;                  // filled in step 2; the D = 64 finish kernel reads its dq / q_hat fields
 
   // dk/dv accumulators of shared keys/values are per call (the dq accumulator is self-cleaning)
   if (shared_kv) {
@@ -1306,7 +1191,6 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     pa.aug = Cfg::kAug ? ws + w.aug_off : nullptr;
     pa.ones = ws + w.ones_off;
     pa.inv_c1 = 1.0f / (h.scale * log2e);
-    pa.dq = Cfg::kFuseFinish ? h.dq.ptr : nullptr; pa.dq_sb = h.dq.sb; pa.dq_sh = h.dq.sh; pa.dq_sn = h.dq.sn;
     const int rows_per_block = 2 * (256 / (D / 8));
     const int padded = w.nqt * Cfg::QT;
     pa.bpb = (padded + rows_per_block - 1) / rows_per_block;
@@ -1342,7 +1226,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
         return FCSA_ERR_INVALID;
       }
     }
-    BwdArgs a;
+    BwdArgs& a = main_args;
     a.B = h.B; a.H = h.H; a.Nq = h.Nq; a.Nk = h.Nk; a.kv_heads = h.kv_heads; a.causal = h.causal;
     a.has_mask = h.mask ? 1 : 0; a.nqt = w.nqt;
     a.c1 = h.scale * log2e; a.scale = h.scale;
@@ -1355,7 +1239,6 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     a.G = h.groups;
     a.bias = h.bias; a.bias_sb = h.bias_sb; a.bias_sh = h.bias_sh; a.bias_sn = h.bias_sn;
     a.dbias = h.dbias; a.dbias_sb = h.dbias_sb; a.dbias_sh = h.dbias_sh;
-    a.cnt = cnt;
     a.dq = h.dq.ptr; a.dq_sb = h.dq.sb; a.dq_sh = h.dq.sh; a.dq_sn = h.dq.sn;
     a.q_hat = h.q.ptr; a.q_sb = h.q.sb; a.q_sh = h.q.sh; a.q_sn = h.q.sn;
     a.q_rnorm = h.q_rnorm;
@@ -1376,13 +1259,14 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.dq_acc = dq_acc; fa.dq = h.dq.ptr; fa.sb = h.dq.sb; fa.sh = h.dq.sh; fa.sn = h.dq.sn;
     fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
     fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
-    if (!Cfg::kFuseFinish) {           // D = 64 converts its dq tiles inside the main kernel
-      if (h.ev_finish[0]) cudaEventRecord(h.ev_finish[0], stream);
-      e = launch_pdl(bwd_dq_finish128_kernel<T>, dim3((unsigned)((long long)h.B * h.H * w.nqt)), dim3(256), 0, stream, fa);
-      if (h.ev_finish[1]) cudaEventRecord(h.ev_finish[1], stream);
-      if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
-      ++*launches;
-    }
+    const long long tiles = (long long)h.B * h.H * w.nqt;
+    if (tiles > 0x7FFFFFFFLL) { *err = "problem too large for one launch"; return FCSA_ERR_INVALID; }
+    if (h.ev_finish[0]) cudaEventRecord(h.ev_finish[0], stream);
+    if (D == 64) e = launch_pdl(bwd_dq_finish64_kernel<T>, dim3((unsigned)tiles), dim3(512), 0, stream, main_args);
+    else e = launch_pdl(bwd_dq_finish128_kernel<T>, dim3((unsigned)tiles), dim3(256), 0, stream, fa);
+    if (h.ev_finish[1]) cudaEventRecord(h.ev_finish[1], stream);
+    if (e != cudaSuccess) { *err = "dq finish launch"; *ce = e; return FCSA_ERR_CUDA; }
+    ++*launches;
     if (shared_kv) {
       for (int which = 0; which < 2; ++which) {
         KvFinishArgs ka;

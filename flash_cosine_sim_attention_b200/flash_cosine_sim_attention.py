@@ -110,6 +110,7 @@ def _ext():
     global _ext_module
     if _ext_module is not None:
         return _ext_module
+    import importlib
     import importlib.machinery
     import importlib.util
     import os
@@ -124,6 +125,12 @@ def _ext():
         if os.path.exists(path):
             break
     else:
+        try:                                     # pip-installed: the module sits top-level, like the reference's
+            _abi.load()
+            _ext_module = importlib.import_module(name)
+            return _ext_module
+        except ImportError:
+            pass
         raise ImportError(
             f"{name} (the torch extension module over libfcsa_b200.so) is not built in {here}: run "
             "`python -m flash_cosine_sim_attention_b200.build` (needs nvcc and g++; sm_100a only).  "
@@ -334,6 +341,83 @@ def plain_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
     return out.squeeze(1) if merged else out
 
 
+# --------------------------------------------------------------------------------------------
+# float32 inputs (reference: Float is dispatched in forward and backward, cu:1702-1703, 1832-1834; half of
+# its test grid is f32, tests/test.py:33-35).  The tcgen05 kernels take 16-bit operands, so float32
+# tensors run on the SAME fused fp16 kernels at tf32-class operand precision - fp16 and tf32 share the
+# 11-bit significand - with fp32 accumulation throughout:
+#   * q, k are l2-normalised in fp32 first (|q_hat|, |k_hat| <= 1 sit comfortably in fp16), then rounded;
+#   * v and the incoming gradient are scaled by a power of two computed ON THE DEVICE from their max
+#     magnitude (exact, undone afterwards), so fp16's narrower exponent range never clips them;
+#   * o, dq, dk, dv come back as float32 (one rounding to 11 bits at the kernels' output).
+# Every op around the kernels is an asynchronous elementwise torch op: no host synchronisation.
+# --------------------------------------------------------------------------------------------
+def _pow2_scale(t, top_exp):
+    """Power of two s (0-dim fp32 tensor, on t's device) with amax|t| / s in [2^(top_exp-1), 2^top_exp)."""
+    amax = t.detach().abs().amax().float().clamp_min(1e-30)
+    return torch.exp2(torch.floor(torch.log2(amax)) + 1 - top_exp)
+
+
+class _GradScaleDown(Function):
+    """Identity forward.  Backward: divides the incoming fp32 gradient by a power of two that brings its
+    largest magnitude to ~2^10 (stored in `holder` for _GradScaleUp) before it is cast to fp16."""
+
+    @staticmethod
+    def forward(ctx, x, holder):
+        ctx.holder = holder
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        s = _pow2_scale(g, 10)
+        ctx.holder.s = s
+        return g / s, None
+
+
+class _GradScaleUp(Function):
+    """Identity forward.  Backward: multiplies the (fp32-cast) gradient back by the scale _GradScaleDown chose."""
+
+    @staticmethod
+    def forward(ctx, x, holder):
+        ctx.holder = holder
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.holder.s, None
+
+
+class _Holder:
+    s = None
+
+
+def _float32_on_half_kernels(q, k, v, mask, attn_bias, scale, groups, causal, l2norm_qk, attn_bias_batch_dim):
+    D = q.shape[-1]
+    assert D % groups == 0, "groups must divide the head dim"
+    h = torch.float16
+    if l2norm_qk:
+        q, k = _l2norm_torch(q, groups), _l2norm_torch(k, groups)           # fp32, differentiable
+    sv = _pow2_scale(v, 8)                                                   # |v / sv| < 256
+    holder = _Holder()
+    up = lambda t: _GradScaleUp.apply(t, holder)
+    qh, kh, vh = up(q).to(h), up(k).to(h), up(v / sv).to(h)
+    if D not in _KERNEL_HEAD_DIMS:
+        # head dims 16 / 32 / 96 (reference cu:84): zero-padded features, as for 16-bit inputs
+        Dp = 64 if D < 64 else 128
+        qh, kh, vh = (torch.nn.functional.pad(t, (0, Dp - D)) for t in (qh, kh, vh))
+    shift = _choose_shift(h, scale, groups if l2norm_qk else 1, l2norm_qk)
+    if exists(attn_bias):
+        bias_h = up(attn_bias).to(h)
+        amax = attn_bias.detach().amax().float().reshape(1) if l2norm_qk else None
+        oh = FlashCosineSimAttention.apply(qh, kh, vh, mask, bias_h, float(scale), bool(causal),
+                                           bool(attn_bias_batch_dim), float(shift), amax)
+    else:
+        oh = _FusedCosineSimAttention.apply(qh, kh, vh, mask, float(scale), bool(causal), 1, False,
+                                            int(groups) if l2norm_qk else 0)
+    o = _GradScaleDown.apply(oh[..., :D].float(), holder)
+    return o * sv
+
+
 _warned = set()
 
 
@@ -346,7 +430,12 @@ def _warn_once(key, msg):
 def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, groups=1, causal=False,
                                l2norm_qk=True, attn_bias_batch_dim=False, l2norm_groups=None):
     """Fused cosine-similarity attention (reference py:308-334, same arguments and meaning;
-    `l2norm_groups` is accepted as an alias of `groups`)."""
+    `l2norm_groups` is accepted as an alias of `groups`).
+
+    Every supported input runs the hand-written sm_100a kernels: float16 / bfloat16 natively, float32 at
+    tf32-class operand precision on the fp16 kernels (see _float32_on_half_kernels), head dims 64 and 128
+    natively and 16 / 32 / 96 (any multiple of 8 below 128) on zero-padded features.  Anything else raises:
+    there is no un-fused or CPU fallback."""
     if exists(l2norm_groups):
         groups = l2norm_groups
     assert not (causal and exists(mask)), "mask should not be supplied if causality is needed"
@@ -355,9 +444,20 @@ def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
             "flash_cosine_sim_attention: CUDA tensors required - this build has no CPU path "
             "(use plain_cosine_sim_attention on CPU tensors)")
     D = q.shape[-1]
-    if (q.dtype in _KERNEL_DTYPES and k.dtype == q.dtype and v.dtype == q.dtype and not exists(attn_bias)
-            and D not in _KERNEL_HEAD_DIMS and D < 128 and D % 8 == 0 and D % groups == 0):
-        # Head dims the kernels are not instantiated for (the reference's 32 and 96): zero-pad the
+    if not (k.dtype == q.dtype and v.dtype == q.dtype):
+        raise TypeError("flash_cosine_sim_attention: q, k, v must share one dtype")
+    if D > 128 or D % 8 != 0 or D % groups != 0:
+        raise NotImplementedError(
+            f"flash_cosine_sim_attention: head_dim {D} with groups {groups} has no sm_100a kernel (head dims: multiples "
+            "of 8 up to 128; the reference supports 16, 32, 64, 96, 128 - cu:84)")
+    if exists(attn_bias) and not attn_bias.is_cuda:
+        raise RuntimeError("flash_cosine_sim_attention: attn_bias must be a CUDA tensor")
+    if q.dtype == torch.float32:
+        return _float32_on_half_kernels(q, k, v, mask, attn_bias, scale, groups, causal, l2norm_qk, attn_bias_batch_dim)
+    if q.dtype not in _KERNEL_DTYPES:
+        raise TypeError(f"flash_cosine_sim_attention: dtype {q.dtype} is not supported (float16, bfloat16, float32)")
+    if D not in _KERNEL_HEAD_DIMS:
+        # Head dims the kernels are not instantiated for (the reference's 16, 32 and 96): zero-pad the
         # features to 64 / 128 and run the same tcgen05 kernels.  Zero features change neither q.k nor
         # the norms (the l2norm runs first, on the real features), the padded output columns are
         # zero and sliced off; autograd takes care of the slices.  Costs two pad copies per tensor.
@@ -365,11 +465,17 @@ def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
         if l2norm_qk:
             q, k = _l2norm_torch(q, groups), _l2norm_torch(k, groups)
         pad = lambda t: torch.nn.functional.pad(t, (0, Dp - D))
-        o = _FusedCosineSimAttention.apply(pad(q), pad(k), pad(v), mask, float(scale), bool(causal), 1, False,
-                                           int(groups) if l2norm_qk else 0)
+        if exists(attn_bias):
+            shift = _choose_shift(q.dtype, scale, groups if l2norm_qk else 1, l2norm_qk)
+            amax = (attn_bias.detach().amax().float().reshape(1)
+                    if (q.dtype == torch.float16 and l2norm_qk) else None)
+            o = FlashCosineSimAttention.apply(pad(q), pad(k), pad(v), mask, attn_bias, float(scale), bool(causal),
+                                              bool(attn_bias_batch_dim), float(shift), amax)
+        else:
+            o = _FusedCosineSimAttention.apply(pad(q), pad(k), pad(v), mask, float(scale), bool(causal), 1, False,
+                                               int(groups) if l2norm_qk else 0)
         return o[..., :D]
-    if (exists(attn_bias) and q.dtype in _KERNEL_DTYPES and k.dtype == q.dtype and v.dtype == q.dtype
-            and D in _KERNEL_HEAD_DIMS and D % groups == 0 and attn_bias.is_cuda):
+    if exists(attn_bias):
         # additive bias: l2norm kernels (with their own backward), then the BIAS instantiations of the
         # attention kernels; d_bias is reduced in fp32 and returned in the bias's dtype
         if l2norm_qk:
@@ -382,16 +488,6 @@ def flash_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
             amax = attn_bias.detach().amax().float().reshape(1)
         return FlashCosineSimAttention.apply(q, k, v, mask, attn_bias, float(scale), bool(causal),
                                              bool(attn_bias_batch_dim), float(shift), amax)
-    if not _kernel_supported(q, k, v, attn_bias):
-        # float32 inputs and head dims above 128 / not a multiple of 8 have no sm_100a kernel yet:
-        # they run the un-fused formulation on the same GPU (correct, slower), never silently wrong.
-        why = ("attn_bias" if exists(attn_bias) else
-               f"dtype {q.dtype}" if q.dtype not in _KERNEL_DTYPES else f"head_dim {q.shape[-1]}")
-        _warn_once(why, f"flash_cosine_sim_attention: no fused sm_100a kernel for {why}; "
-                        "running the un-fused GPU formulation")
-        return plain_cosine_sim_attention(q, k, v, mask=mask, attn_bias=attn_bias, scale=scale,
-                                          groups=groups, causal=causal, l2norm_qk=l2norm_qk,
-                                          attn_bias_batch_dim=attn_bias_batch_dim)
     gs = q.shape[-1] // groups
-    assert q.shape[-1] % groups == 0 and (gs & (gs - 1)) == 0, "groups must divide the head dim into power-of-two chunks"
+    assert (gs & (gs - 1)) == 0, "groups must divide the head dim into power-of-two chunks"
     return _FusedCosineSimAttention.apply(q, k, v, mask, float(scale), bool(causal), int(groups), bool(l2norm_qk))

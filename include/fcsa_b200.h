@@ -97,12 +97,12 @@ int fcsa_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tensor*
  * contents irrelevant on entry, garbage on exit. */
 size_t fcsa_backward_workspace_bytes(const fcsa_problem* p);
 
-/* Bytes of the ZEROED workspace of fcsa_backward (fp32 dq accumulator tiles + per-tile arrival counters).
+/* Bytes of the ZEROED workspace of fcsa_backward (the fp32 dq accumulator tiles).
  * Contract: every byte is zero when a backward call starts and zero again when its kernels have
- * finished - whoever converts an accumulator tile to dq also clears it - so one buffer, zero-filled
- * ONCE (fcsa_zeroed_init), serves any number of calls of any shape enqueued on the same stream.
- * This is what replaces the reference's per-call 33.5 MB memset of its fp32 dq (cu:1818) and its
- * separate cast pass (cu:1904).  Do not share one buffer between streams that may run concurrently. */
+ * finished - the pass that converts an accumulator tile to dq also clears it - so one buffer,
+ * zero-filled ONCE (fcsa_zeroed_init), serves any number of calls of any shape enqueued on the same
+ * stream.  This is what replaces the reference's per-call 33.5 MB memset of its fp32 dq (cu:1818).
+ * Do not share one buffer between streams that may run concurrently. */
 size_t fcsa_backward_zeroed_bytes(const fcsa_problem* p);
 
 /* Zero-fill a freshly allocated (or grown) zeroed workspace: cudaMemsetAsync on `stream`. */

@@ -32,3 +32,26 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Achieved parity errors (worst case per dtype and quantity, relative to max|reference|), next to the
+    tolerance they were tested against - also written to gpurun_out/parity_errors.json."""
+    try:
+        from tests import test_gpu_parity as tp
+    except Exception:       # noqa: BLE001
+        try:
+            import test_gpu_parity as tp
+        except Exception:   # noqa: BLE001
+            return
+    if not getattr(tp, "ERRORS", None):
+        return
+    import json
+    terminalreporter.write_line("achieved parity errors (max |got - ref| / max |ref|):")
+    for key in sorted(tp.ERRORS):
+        e = tp.ERRORS[key]
+        terminalreporter.write_line(f"  {key:14s} {e['max_err']:.3e}   (tolerance {e['tol']:.0e})")
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump(tp.ERRORS, f, indent=1, sort_keys=True)

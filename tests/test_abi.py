@@ -83,13 +83,12 @@ def test_workspace_size_formula(lib):
     n = lib.fcsa_backward_workspace_bytes(_abi.ref(p))
     stats = 4 * 8 * 32 * 256 * 4
     dq = 4 * 8 * 4096 * 64 * 4
-    cnt = 4 * 8 * 32 * 4                    # one arrival counter per 128-row query tile
     aug = 4 * 8 * 4096 * 32 * 2 + 4096      # 16-bit slivers of the augmented contraction + the ones tile
     assert n == stats + aug                 # scratch: per-row constants only
-    assert lib.fcsa_backward_zeroed_bytes(_abi.ref(p)) == dq + cnt      # self-cleaning: dq accumulator + counters
+    assert lib.fcsa_backward_zeroed_bytes(_abi.ref(p)) == dq            # self-cleaning fp32 dq accumulator
     p.kv_heads = 1
     assert lib.fcsa_backward_workspace_bytes(_abi.ref(p)) == stats + aug + 2 * 4 * 4096 * 64 * 4
-    assert lib.fcsa_backward_zeroed_bytes(_abi.ref(p)) == dq + cnt
+    assert lib.fcsa_backward_zeroed_bytes(_abi.ref(p)) == dq
 
 
 def test_backward_rejects_missing_zeroed_workspace(lib):
