@@ -163,32 +163,47 @@ __device__ __forceinline__ void split3(float x, uint32_t& w01, uint32_t& w2) {
   w2 = pack2<T>(e2, 0.f);
 }
 
-template <typename T>
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// TPR = threads per row = D / 8 (8 or 16); QT is 128 (D = 64) or 64 (D = 128).
+template <typename T, int TPR>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
-  // 1-D grid = batch*heads x (row blocks of the padded sequence); D/8 threads per row, two rows per
-  // thread (four 16-byte loads in flight), shuffle reduce.  No per-thread integer division on the address path.
+  // 1-D grid = batch*heads x (row blocks of the padded sequence); TPR threads per row, two rows per
+  // thread (four 16-byte loads in flight), shuffle reduce.  The pass must stay memory-bound (33.5 MB in, 8 MB
+  // out at the metric shape): no runtime-divisor divisions, MUFU log2, the 64-byte sliver row of a query
+  // written by four lanes instead of one.
   pdl_launch_dependents();
   pdl_wait();
-  const int tpr = a.D >> 3;
-  const int rpb = 256 / tpr;                 // rows per block and pass
+  constexpr int RPB = 256 / TPR;             // rows per block and pass
+  constexpr int QT = (TPR == 8) ? 128 : 64;
+  constexpr int QSH = (TPR == 8) ? 7 : 6;
   const int bh = blockIdx.x / a.bpb;
   const int blk = blockIdx.x - bh * a.bpb;
   const int b = bh / a.H, h = bh - b * a.H;
-  const int tr = threadIdx.x % tpr;
-  const int padded = a.nqt * a.QT;
+  const int tr = threadIdx.x % TPR;
+  const int padded = a.nqt * QT;
   const float c2 = a.c2 + (a.shift_extra != nullptr ? fmaxf(__ldg(a.shift_extra), 0.f) * 1.4426950408889634f : 0.f);
+  const T* obase = reinterpret_cast<const T*>(a.o) + b * a.o_sb + h * a.o_sh + tr * 8;
+  const T* dbase = reinterpret_cast<const T*>(a.d_o) + b * a.do_sb + h * a.do_sh + tr * 8;
   int row[2];
   bool in[2], valid[2];
   uint4 ro[2], rd[2];
+  float il[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    row[u] = (blk * 2 + u) * rpb + threadIdx.x / tpr;     // row inside the padded (nqt*QT) range
+    row[u] = (blk * 2 + u) * RPB + threadIdx.x / TPR;     // row inside the padded (nqt*QT) range
     in[u] = row[u] < padded;
     valid[u] = in[u] && row[u] < a.Nq;
     ro[u] = rd[u] = make_uint4(0, 0, 0, 0);
+    il[u] = 1.f;
     if (valid[u]) {
-      ro[u] = ldg_stream128(reinterpret_cast<const T*>(a.o) + b * a.o_sb + h * a.o_sh + (long long)row[u] * a.o_sn + tr * 8);
-      rd[u] = ldg_stream128(reinterpret_cast<const T*>(a.d_o) + b * a.do_sb + h * a.do_sh + (long long)row[u] * a.do_sn + tr * 8);
+      ro[u] = ldg_stream128(obase + (long long)row[u] * a.o_sn);
+      rd[u] = ldg_stream128(dbase + (long long)row[u] * a.do_sn);
+      if (tr == 0) il[u] = __ldg(a.inv_l + (long long)bh * a.Nq + row[u]);
     }
   }
 #pragma unroll
@@ -197,27 +212,27 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
     const float2 b0 = unpack2<T>(rd[u].x), b1 = unpack2<T>(rd[u].y), b2 = unpack2<T>(rd[u].z), b3 = unpack2<T>(rd[u].w);
     float dot = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y +
                 a3.x * b3.x + a3.y * b3.y;
-    for (int m = 1; m < tpr; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
+#pragma unroll
+    for (int m = 1; m < TPR; m <<= 1) dot += __shfl_xor_sync(0xFFFFFFFFu, dot, m);
+    // lane tr == 0 of the row holds inv_l: c3 = log2(inv_l) - shift*log2e, broadcast to the row's lanes
+    float c3 = valid[u] ? lg2_approx(il[u]) - c2 : 0.f;
+    c3 = __shfl_sync(0xFFFFFFFFu, c3, (threadIdx.x & 31) & ~(TPR - 1));
+    const float ndl = valid[u] ? -dot : 0.f;      // stored negated: the dS stage computes P * (dP + (-delta))
     if (!in[u]) continue;
-    const int qt = row[u] / a.QT, r = row[u] - qt * a.QT;
-    if (tr != 0) continue;
-    float* st = a.stats + ((long long)bh * a.nqt + qt) * 2 * a.QT;
-    float c3 = 0.f, dl = 0.f;
-    if (valid[u]) {
-      c3 = log2f(a.inv_l[(long long)bh * a.Nq + row[u]]) - c2;
-      dl = dot;
-    }
-    st[r] = c3;
-    st[a.QT + r] = -dl;      // stored negated: the dS stage computes P * (dP + (-delta)) with packed adds
     if (a.aug) {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.aug) + ((long long)bh * padded + row[u]) * 64);
-      uint4 s0 = make_uint4(0, 0, 0, 0), d0 = s0;
-      if (valid[u]) {
-        split3<T>(c3 * a.inv_c1, s0.x, s0.y);
-        split3<T>(-dl, d0.x, d0.y);
+      // D = 64: the 64-byte sliver row {c3/c1 in three 16-bit parts, 0.., -delta in three parts, 0..}; lanes 0..3
+      // of the row write one 16-byte quarter each
+      if (tr < 4) {
+        uint4 q4 = make_uint4(0, 0, 0, 0);
+        if (valid[u] && (tr & 1) == 0) split3<T>(tr == 0 ? c3 * a.inv_c1 : ndl, q4.x, q4.y);
+        reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.aug) + ((long long)bh * padded + row[u]) * 64)[tr] = q4;
       }
-      dst[0] = s0; dst[1] = make_uint4(0, 0, 0, 0);
-      dst[2] = d0; dst[3] = make_uint4(0, 0, 0, 0);
+    } else if (tr == 0) {
+      // D = 128: fp32 {c3, -delta} per query tile, read by the main kernel through shared memory
+      const int qt = row[u] >> QSH, r = row[u] & (QT - 1);
+      float* st = a.stats + ((long long)bh * a.nqt + qt) * 2 * QT;
+      st[r] = c3;
+      st[QT + r] = ndl;
     }
   }
   if (a.aug && blockIdx.x == 0 && threadIdx.x < 128) {
@@ -265,6 +280,9 @@ __device__ __forceinline__ uint32_t ldg_u16(const void* p) {
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // 16-byte load served by L2 (never a stale L1 line): accumulator tiles other CTAs have reduced into
 __device__ __forceinline__ float4 ldg_cg128f(const float* p) {
@@ -694,15 +712,29 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       tmem_ld_x16(tDQ, dqv);
       tmem_ld_wait();
+#ifdef FCSA_EXP_RED_V4
+      {
+        // straight from registers: four 16-byte vector reductions per thread, 512 contiguous bytes per warp
+        float* dst = a.dq_acc + (((long long)bh * a.nqt + (i_lo + j)) * 4 + wq) * 2048 + wg * 512 + lane * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          red_add_v4_f32(dst + c * 128, __uint_as_float(dqv[4 * c]), __uint_as_float(dqv[4 * c + 1]),
+                         __uint_as_float(dqv[4 * c + 2]), __uint_as_float(dqv[4 * c + 3]));
+      }
+#else
       // the previous bulk reduce must have finished reading the staging buffer
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         sts128(my_stage + c * 512 + lane * 16, dqv[4 * c], dqv[4 * c + 1], dqv[4 * c + 2], dqv[4 * c + 3]);
+#endif
     };
     // after a fence.proxy.async: staged dQ of tile j -> global accumulator (TMA reduce-add, 2 KB)
     auto reduce_dq = [&](int j) {
+#ifdef FCSA_EXP_RED_V4
+      return;
+#endif
       __syncwarp();
 #ifndef FCSA_EXP_SKIP_REDUCE
       if (lane == 0) {
@@ -1197,7 +1229,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     const long long grid = (long long)pa.bpb * h.B * h.H;
     if (grid > 0x7FFFFFFFLL) { *err = "problem too large for one launch"; return FCSA_ERR_INVALID; }
     if (h.ev_prep[0]) cudaEventRecord(h.ev_prep[0], stream);
-    e = launch_pdl(bwd_prep_kernel<T>, dim3((unsigned)grid), dim3(256), 0, stream, pa);
+    e = launch_pdl(bwd_prep_kernel<T, D / 8>, dim3((unsigned)grid), dim3(256), 0, stream, pa);
     if (h.ev_prep[1]) cudaEventRecord(h.ev_prep[1], stream);
     if (e != cudaSuccess) { *err = "backward preprocess launch"; *ce = e; return FCSA_ERR_CUDA; }
     ++*launches;

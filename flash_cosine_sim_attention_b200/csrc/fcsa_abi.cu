@@ -350,7 +350,7 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   float* rn[2] = {n->q_rnorm, n->k_rnorm};
   const int heads[2] = {p->heads, p->kv_heads};
   const int rows[2] = {p->seq_q, p->seq_k};
-  int max_rows = 0, max_bh = 0;
+  int max_rows = 0;
   for (int t = 0; t < 2; ++t) {
     fcsa::L2Args& a = pa.t[t];
     a.B = p->batch; a.H = heads[t]; a.N = rows[t]; a.D = p->head_dim; a.G = n->groups;
@@ -358,16 +358,14 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
     a.y_sb = dst[t]->sb; a.y_sh = dst[t]->sh; a.y_sn = dst[t]->sn;
     a.x = src[t]->ptr; a.y = dst[t]->ptr; a.rnorm = rn[t];
     if (a.N > max_rows) max_rows = a.N;
-    if (a.B * a.H > max_bh) max_bh = a.B * a.H;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  constexpr int U = 4;                                       // rows per thread per work item
-  const int rows_per_item = U * (256 / (p->head_dim / 8));
-  long long items = 0;
-  for (int t = 0; t < 2; ++t)
-    items += (long long)pa.t[t].B * pa.t[t].H * ((pa.t[t].N + rows_per_item - 1) / rows_per_item);
-  const long long persistent = (long long)sm_count() * 4;    // resident CTAs: 4 x 256 threads per SM
-  dim3 grid((unsigned)(items < persistent ? (items > 0 ? items : 1) : persistent));
+  constexpr int U = 2;                                       // rows per thread
+  const int rows_per_block = U * (256 / (p->head_dim / 8));
+  const long long bhs = (long long)pa.t[0].B * pa.t[0].H + (long long)pa.t[1].B * pa.t[1].H;
+  if (bhs > 65535) return fail(FCSA_ERR_UNSUPPORTED, "fused l2norm: batch*heads of q plus k exceeds 65535 - "
+                                                    "normalise with fcsa_l2norm_forward and call fcsa_forward");
+  dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), (unsigned)bhs);
   cudaError_t e;
   const bool bf = p->dtype == FCSA_BF16;
   if (g_ev[2][0]) cudaEventRecord(g_ev[2][0], s);

@@ -21,6 +21,15 @@ struct L2Args {
   float* rnorm;                   // (B, H, N, G) fp32
 };
 
+// 1 / max(sqrt(ss), 1e-12)  (py:38-55: F.normalize's eps) = min(rsqrt(ss), 1e12): one MUFU.RSQ instead of an
+// IEEE sqrt + divide (~60 instructions per row and thread in a pass that must stay HBM-bound); the
+// approximation error (2^-22) vanishes under the 16-bit rounding of the normalised output
+__device__ __forceinline__ float rnorm_of(float ss) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ss));
+  return fminf(r, 1e12f);
+}
+
 // sum over the `tpg` consecutive lanes that share a group (tpg is a power of two <= 16)
 __device__ __forceinline__ float group_reduce(float v, int tpg) {
   for (int m = 1; m < tpg; m <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, m);
@@ -68,7 +77,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
     for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
     const int tpg = gs >> 3;
     ss = group_reduce(ss, tpg);
-    const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    const float r = rnorm_of(ss);
 #pragma unroll
     for (int i = 0; i < 8; ++i) rn[i] = r;
     if (ok && a.rnorm && (tr % tpg) == 0) a.rnorm[row * a.G + tr / tpg] = r;
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
     subgroup_sums8(sq, gs, ss);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      rn[i] = 1.0f / fmaxf(sqrtf(ss[i]), 1e-12f);
+      rn[i] = rnorm_of(ss[i]);
       if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = rn[i];
     }
   }
@@ -95,117 +104,82 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
   }
 }
 
-// q and k in one launch (blockIdx.y selects the tensor), two rows per thread so that two
-// independent 16-byte loads are in flight before the first reduction.
+// q and k in one launch.  grid = (row blocks, batch*heads of q + batch*heads of k): blockIdx.y selects the
+// tensor and its (batch, head), so no thread divides 64-bit indices; one thread owns 8 features of U rows
+// and issues its U 16-byte loads before the first reduction.  TPR = threads per row (D / 8) when known at
+// compile time (8 or 16), 0 = read it from the arguments.  A short-lived-CTA grid (many waves of small CTAs,
+// 8 resident per SM) measured faster here than a persistent loop: the per-item bookkeeping of the loop
+// (item decode with 64-bit divisions, register copies of the prefetched rows) cost more instructions than the
+// rows themselves (profiles/r02_aux_kernels.txt).
 struct L2PairArgs {
   L2Args t[2];
 };
 
-// TPR = threads per row (D / 8) when known at compile time (8 or 16), 0 = read it from the
-// arguments; U = rows per thread per work item.  Persistent: a fixed grid (a few CTAs per SM)
-// strides over the work items (tensor, batch*head, block of U * 256/TPR rows), and the U 16-byte
-// loads of the NEXT item are issued before the current item is reduced and stored, so every SM
-// always has loads in flight (an HBM-bound pass needs ~40 KB in flight per SM to reach the copy
-// rate; short-lived CTAs spend their life ramping up).
 template <typename T, int TPR, int U>
-__global__ void __launch_bounds__(256, 4) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
+__global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
   pdl_launch_dependents();
   pdl_wait();
-  const int tpr = TPR ? TPR : (pa.t[0].D >> 3);
-  const int rows_per_item = U * (256 / tpr);
+  const int bh0 = pa.t[0].B * pa.t[0].H;
+  const int which = blockIdx.y >= bh0;
+  const L2Args& a = pa.t[which];
+  const int bh = blockIdx.y - (which ? bh0 : 0);
+  const int tpr = TPR ? TPR : (a.D >> 3);
+  const int rpp = 256 / tpr;                          // rows per pass
   const int tr = threadIdx.x % tpr;
   const int r_in = threadIdx.x / tpr;
-  const int nb0 = (pa.t[0].N + rows_per_item - 1) / rows_per_item;
-  const int nb1 = (pa.t[1].N + rows_per_item - 1) / rows_per_item;
-  const long long cnt0 = (long long)pa.t[0].B * pa.t[0].H * nb0;
-  const long long total = cnt0 + (long long)pa.t[1].B * pa.t[1].H * nb1;
-
-  struct Item { int t, bh, row0; };
-  auto decode = [&](long long w) {
-    Item it;
-    it.t = w >= cnt0;
-    const long long v = it.t ? w - cnt0 : w;
-    const int nb = it.t ? nb1 : nb0;
-    it.bh = (int)(v / nb);
-    it.row0 = (int)(v - (long long)it.bh * nb) * rows_per_item;
-    return it;
-  };
-  auto load = [&](const Item& it, uint4 (&raw)[U]) {
-    const L2Args& a = pa.t[it.t];
-    const int b = it.bh / a.H, h = it.bh - b * a.H;
-    const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 8;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int n = it.row0 + u * (256 / tpr) + r_in;
-      raw[u] = make_uint4(0, 0, 0, 0);
-      if (n < a.N) raw[u] = ldg_stream128(xbase + (long long)n * a.x_sn);
-    }
-  };
-
-  long long w = blockIdx.x;
-  if (w >= total) return;
-  Item cur = decode(w);
+  const int row0 = blockIdx.x * (U * rpp);
+  if (row0 >= a.N) return;                            // the grid is sized for the longer of the two tensors
+  const int b = bh / a.H, h = bh - b * a.H;
+  const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 8;
+  T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 8;
   uint4 raw[U];
-  load(cur, raw);
-  while (true) {
-    const long long wn = w + gridDim.x;
-    const bool more = wn < total;
-    Item nxt = cur;
-    uint4 raw_n[U];
-    if (more) {
-      nxt = decode(wn);
-      load(nxt, raw_n);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int n = row0 + u * rpp + r_in;
+    raw[u] = make_uint4(0, 0, 0, 0);
+    if (n < a.N) raw[u] = ldg_stream128(xbase + (long long)n * a.x_sn);
+  }
+  const int gs = a.D / a.G;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int n = row0 + u * rpp + r_in;
+    const bool ok = n < a.N;
+    const long long row = (long long)bh * a.N + n;
+    float f[8];
+    {
+      float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
+      f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y; f[4] = t2.x; f[5] = t2.y; f[6] = t3.x; f[7] = t3.y;
     }
-    const L2Args& a = pa.t[cur.t];
-    const int b = cur.bh / a.H, h = cur.bh - b * a.H;
-    const int gs = a.D / a.G;
-    T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 8;
+    float rn[8];
+    if (gs >= 8) {
+      float ss = 0.f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int n = cur.row0 + u * (256 / tpr) + r_in;
-      const bool ok = n < a.N;
-      const long long row = (long long)cur.bh * a.N + n;
-      float f[8];
-      {
-        float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
-        f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y; f[4] = t2.x; f[5] = t2.y; f[6] = t3.x; f[7] = t3.y;
-      }
-      float rn[8];
-      if (gs >= 8) {
-        float ss = 0.f;
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+      const int tpg = gs >> 3;
+      ss = group_reduce(ss, tpg);
+      const float r = rnorm_of(ss);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-        const int tpg = gs >> 3;
-        ss = group_reduce(ss, tpg);
-        const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      for (int i = 0; i < 8; ++i) rn[i] = r;
+      if (ok && a.rnorm && (tr & (tpg - 1)) == 0) a.rnorm[row * a.G + tr / tpg] = r;
+    } else {
+      float sq[8], ss[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rn[i] = r;
-        if (ok && a.rnorm && (tr & (tpg - 1)) == 0) a.rnorm[row * a.G + tr / tpg] = r;
-      } else {
-        float sq[8], ss[8];
+      for (int i = 0; i < 8; ++i) sq[i] = f[i] * f[i];
+      subgroup_sums8(sq, gs, ss);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sq[i] = f[i] * f[i];
-        subgroup_sums8(sq, gs, ss);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rn[i] = 1.0f / fmaxf(sqrtf(ss[i]), 1e-12f);
-          if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = rn[i];
-        }
-      }
-      if (ok) {
-        uint4 wv;
-        wv.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
-        wv.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
-        wv.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
-        wv.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
-        *reinterpret_cast<uint4*>(ybase + (long long)n * a.y_sn) = wv;
+      for (int i = 0; i < 8; ++i) {
+        rn[i] = rnorm_of(ss[i]);
+        if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = rn[i];
       }
     }
-    if (!more) break;
-    w = wn;
-    cur = nxt;
-#pragma unroll
-    for (int u = 0; u < U; ++u) raw[u] = raw_n[u];
+    if (ok) {
+      uint4 wv;
+      wv.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
+      wv.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
+      wv.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
+      wv.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
+      *reinterpret_cast<uint4*>(ybase + (long long)n * a.y_sn) = wv;
+    }
   }
 }
 

@@ -48,9 +48,9 @@ int main() {
     a.x = t ? k : q; a.y = t ? kn : qn; a.rnorm = t ? rk : rq;
   }
   {
-    dim3 grid(148 * 4);
-    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 4><<<grid, 256>>>(pa); }, 4.0 * n * 2);
-    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 4><<<grid, 256>>>(pa); }, 4.0 * n * 2, false);
+    dim3 grid((N + 63) / 64, 2 * B * H);
+    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 2><<<grid, 256>>>(pa); }, 4.0 * n * 2);
+    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 2><<<grid, 256>>>(pa); }, 4.0 * n * 2, false);
   }
   // prep (per-row constants + slivers; no accumulator zeroing any more)
   {
@@ -62,8 +62,8 @@ int main() {
     const int rows_per_block = 2 * (256 / (D / 8));
     p.bpb = (w.nqt * w.QT + rows_per_block - 1) / rows_per_block;
     dim3 grid(p.bpb * B * H);
-    time_it("bwd_prep (delta, slivers)", [&] { fcsa::bwd_prep_kernel<bf16><<<grid, 256>>>(p); }, 2.0 * n * 2 + (double)B * H * N * 64);
-    time_it("bwd_prep (delta, slivers)", [&] { fcsa::bwd_prep_kernel<bf16><<<grid, 256>>>(p); }, 2.0 * n * 2 + (double)B * H * N * 64, false);
+    time_it("bwd_prep (delta, slivers)", [&] { fcsa::bwd_prep_kernel<bf16, 8><<<grid, 256>>>(p); }, 2.0 * n * 2 + (double)B * H * N * 64);
+    time_it("bwd_prep (delta, slivers)", [&] { fcsa::bwd_prep_kernel<bf16, 8><<<grid, 256>>>(p); }, 2.0 * n * 2 + (double)B * H * N * 64, false);
   }
   // dq conversion (reads the fp32 accumulator + q_hat, writes dq, clears the accumulator)
   {

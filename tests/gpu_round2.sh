@@ -10,9 +10,11 @@ timeout -k 10 120 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1
 timeout -k 10 300 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 timeout -k 10 120 python tests/gpu_cpu_overhead.py > $out/${tag}_overhead.log 2>&1
 timeout -k 10 120 ./tests/cuda/time_bwd > $out/${tag}_time_bwd.log 2>&1
+for v in tests/cuda/time_bwd_*; do [ -x "$v" ] && { echo "variant $v" >> $out/${tag}_time_bwd.log; timeout -k 10 120 $v >> $out/${tag}_time_bwd.log 2>&1; }; done
 timeout -k 10 120 ./tests/cuda/time_fwd > $out/${tag}_time_fwd.log 2>&1
 timeout -k 10 120 ./tests/cuda/bench_aux > $out/${tag}_aux.log 2>&1
-tail -5 $out/${tag}_pytest.log
+if [ -n "$2" ]; then timeout -k 10 1500 python tests/gpu_reference_scripts.py --out $out --only $2 > $out/${tag}_refscripts.log 2>&1; cat $out/${tag}_refscripts.log; fi
+tail -25 $out/${tag}_pytest.log
 cat $out/${tag}_smoke.log | tail -2
 cat $out/${tag}_bench.json | cut -c1-1500
 tail -3 $out/${tag}_bench.err
