@@ -67,8 +67,11 @@ def ext_compile_command(out=None):
     cuda_home = os.environ.get("CUDA_HOME") or os.path.dirname(os.path.dirname(_nvcc()))
     inc = list(ce.include_paths()) + [os.path.join(cuda_home, "include"), sysconfig.get_paths()["include"]]
     libdirs = list(ce.library_paths()) + [os.path.join(cuda_home, "lib64")]
-    cxx = os.environ.get("CXX", "g++")
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+    # the system g++ on PATH, as nvcc uses for the library.  ($CXX in this image points at a wrapped toolchain
+    # under /opt/gcc whose objects crash while unwinding a c10::Error through pybind11 - measured here; set
+    # FCSA_CXX to override)
+    cxx = os.environ.get("FCSA_CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wno-unused-function",
            f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H",
            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
     cmd += [f"-I{d}" for d in inc]

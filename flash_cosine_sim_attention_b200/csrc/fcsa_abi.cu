@@ -363,8 +363,13 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   constexpr int U = 2;                                       // rows per thread
   const int rows_per_block = U * (256 / (p->head_dim / 8));
   const long long bhs = (long long)pa.t[0].B * pa.t[0].H + (long long)pa.t[1].B * pa.t[1].H;
-  if (bhs > 65535) return fail(FCSA_ERR_UNSUPPORTED, "fused l2norm: batch*heads of q plus k exceeds 65535 - "
-                                                    "normalise with fcsa_l2norm_forward and call fcsa_forward");
+  if (bhs > 65535) {
+    // more (batch, head) pairs than grid.y holds (merged batch-heads layouts): one 1-D-grid launch per tensor
+    const bool bf16 = p->dtype == FCSA_BF16;
+    for (int t = 0; t < 2; ++t)
+      if ((r = bf16 ? launch_l2norm_fwd<__nv_bfloat16>(pa.t[t], s) : launch_l2norm_fwd<__half>(pa.t[t], s))) return r;
+    return fcsa_forward(p, &n->q_hat, &n->k_hat, v, o, inv_l, stream);
+  }
   dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), (unsigned)bhs);
   cudaError_t e;
   const bool bf = p->dtype == FCSA_BF16;

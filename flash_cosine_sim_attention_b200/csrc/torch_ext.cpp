@@ -361,4 +361,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("l2norm_forward", &l2norm_forward, "grouped l2norm: x -> (y, 1/norm)");
   m.def("l2norm_backward", &l2norm_backward, "grouped l2norm backward from the normalised y");
   m.def("abi_version", []() { return fcsa_version(); });
+  m.def("_error_path_selftest", []() { FCSA_CHECK(fcsa_forward(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); },
+        "raises the library's error for a null problem (exercises the C ABI error -> Python exception path)");
 }

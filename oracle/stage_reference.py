@@ -8,7 +8,7 @@ with gpurun).  Reference sources are never copied into the tracked tree.
 
   baseline/_ref/                the reference's python package and its own scripts, byte for byte:
       flash_cosine_sim_attention/{__init__,flash_cosine_sim_attention,transformer,benchmark,version}.py
-      tests/test.py  benchmark.py  train.py
+      scripts/{tests/test.py, benchmark.py, train.py}
     used by (a) `bench.py --impl reference`, which times the reference's own plain_cosine_sim_attention on
     the host cores, and (b) tests/gpu_reference_scripts.py, which runs the reference's test-suite,
     benchmark.py and train.py against THIS repo's operator (verdict r1 item 7).
@@ -33,23 +33,27 @@ DST = os.path.join(ROOT, "baseline", "_ref")
 CUDA_DST = os.path.join(HERE, "_ref")
 CUDA_NAME = "flash_cosine_sim_attention_cuda_ref"
 
-FILES = [
-    "flash_cosine_sim_attention/__init__.py",
-    "flash_cosine_sim_attention/flash_cosine_sim_attention.py",
-    "flash_cosine_sim_attention/transformer.py",
-    "flash_cosine_sim_attention/benchmark.py",
-    "flash_cosine_sim_attention/version.py",
-    "tests/test.py",
-    "benchmark.py",
-    "train.py",
-]
+# source (relative to the reference) -> destination (relative to baseline/_ref).  The scripts go into their own
+# directory: python puts a script's directory first on sys.path, and next to the reference's package directory
+# `import flash_cosine_sim_attention` would pick the REFERENCE package (which cannot even be imported without
+# its compiled extension) instead of the drop-in one under test.
+FILES = {
+    "flash_cosine_sim_attention/__init__.py": "flash_cosine_sim_attention/__init__.py",
+    "flash_cosine_sim_attention/flash_cosine_sim_attention.py": "flash_cosine_sim_attention/flash_cosine_sim_attention.py",
+    "flash_cosine_sim_attention/transformer.py": "flash_cosine_sim_attention/transformer.py",
+    "flash_cosine_sim_attention/benchmark.py": "flash_cosine_sim_attention/benchmark.py",
+    "flash_cosine_sim_attention/version.py": "flash_cosine_sim_attention/version.py",
+    "tests/test.py": "scripts/tests/test.py",
+    "benchmark.py": "scripts/benchmark.py",
+    "train.py": "scripts/train.py",
+}
 
 
 def stage_python():
     if not os.path.isdir(REF):
         return False
-    for rel in FILES:
-        src, dst = os.path.join(REF, rel), os.path.join(DST, rel)
+    for rel, out in FILES.items():
+        src, dst = os.path.join(REF, rel), os.path.join(DST, out)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             shutil.copyfile(src, dst)

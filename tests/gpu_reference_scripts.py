@@ -8,9 +8,9 @@
   4. the reference's own CUDA kernel (its .cu compiled for sm_100a by oracle/stage_reference.py --cuda)
      timed at the metric shape next to this repository's kernels: the wmma "kernel to beat"
 
-The scripts come from baseline/_ref/ (staged by oracle/stage_reference.py, git-ignored, byte-identical copies)
-or /root/reference when present; `import flash_cosine_sim_attention` resolves to this repository's drop-in
-package because the repository root is first on PYTHONPATH.  Logs go to --out (default gpurun_out/).
+The scripts come from baseline/_ref/scripts/ (staged by oracle/stage_reference.py, git-ignored, byte-identical
+copies); `import flash_cosine_sim_attention` resolves to this repository's drop-in package because the repository
+root is on PYTHONPATH and the reference's own package does not sit next to the scripts.  Logs go to --out (default gpurun_out/).
 TEST / MEASUREMENT INFRASTRUCTURE ONLY.
 """
 import argparse
@@ -27,9 +27,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def find_reference():
-    for cand in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
-        if os.path.exists(os.path.join(cand, "tests", "test.py")):
-            return cand
+    """Directory holding the reference's scripts WITHOUT its package next to them (a script's own directory comes
+    first on sys.path; the drop-in `flash_cosine_sim_attention` package of this repository must win)."""
+    cand = os.path.join(ROOT, "baseline", "_ref", "scripts")
+    if os.path.exists(os.path.join(cand, "tests", "test.py")):
+        return cand
     return None
 
 
@@ -60,6 +62,26 @@ def run_tests(ref, out):
         by[key] = by.get(key, 0) + 1
     for key in sorted(by):
         print("   failed", key, by[key], flush=True)
+    # The reference compares float32 at atol = 1e-4 (tests/test.py:33,81).  float32 inputs run here at tf32-class
+    # operand precision (11-bit significands, fp32 accumulation), which north_star budgets at 1e-3: the same
+    # grid once more with ONLY the tolerance of the f32 rows changed (a conftest that patches `allclose`).
+    conf = os.path.join(out, "fcsa_f32_tol_plugin.py")
+    with open(conf, "w") as f:
+        f.write("import pytest\n\n@pytest.fixture(autouse=True)\ndef _f32_tolerance_1e3(request, monkeypatch):\n"
+                "    mod = request.module\n    orig = mod.allclose\n"
+                "    monkeypatch.setattr(mod, 'allclose', lambda a, b, atol=1e-4: orig(a, b, atol=max(atol, 1e-3)))\n")
+    cmd2 = [sys.executable, "-m", "pytest", os.path.join(ref, "tests", "test.py"), "-q", "-p", "no:cacheprovider",
+            "-k", "not cpu", "--tb=line", "-c", "/dev/null", "--rootdir", out, "--confcutdir", out,
+            "-p", "fcsa_f32_tol_plugin"]
+    e2 = env()
+    e2["PYTHONPATH"] = out + os.pathsep + e2["PYTHONPATH"]
+    p2 = subprocess.run(cmd2, cwd=out, env=e2, capture_output=True, text=True, timeout=1500)
+    os.remove(conf)
+    text2 = p2.stdout + p2.stderr
+    tail2 = [ln for ln in text2.splitlines() if re.search(r"\d+ (passed|failed)", ln)]
+    with open(log, "a") as f:
+        f.write("\n$ same grid, float32 rows compared at atol 1e-3 instead of 1e-4 (only change: tolerance)\n" + text2[-8000:])
+    print("   with f32 atol 1e-3:", tail2[-1] if tail2 else "no summary", flush=True)
 
 
 def run_benchmark(ref, out):
@@ -114,63 +136,83 @@ def run_train(ref, out, steps=20):
           f"{losses[-1] if losses else None}, finite={ok}", flush=True)
 
 
+REFK_CHILD = r"""
+import importlib.util, json, os, sys, torch
+root, so, what = sys.argv[1], sys.argv[2], sys.argv[3]
+sys.path.insert(0, root)
+spec = importlib.util.spec_from_file_location("flash_cosine_sim_attention_cuda_ref", so)
+refk = importlib.util.module_from_spec(spec); spec.loader.exec_module(refk)
+import flash_cosine_sim_attention_b200 as ours
+from flash_cosine_sim_attention_b200.flash_cosine_sim_attention import backward as our_bwd, forward as our_fwd
+B, H, N, D = 4, 8, 4096, 64
+g = torch.Generator(device="cuda").manual_seed(0)
+q, k, v, do = (torch.randn(B, H, N, D, generator=g, device="cuda", dtype=torch.float16) for _ in range(4))
+qn, kn = ours.l2norm_tensors(q, k)
+def best(fn, n=10):
+    ts = []
+    for _ in range(n + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts[2:]), r
+res = {}
+t, (o_o, l_o, _) = best(lambda: our_fwd(qn, kn, v, None, None, False, 8.0, True)); res["ours_fwd_ms"] = t
+t, g_o = best(lambda: our_bwd(do, o_o, l_o, qn, kn, v, None, None, False, 8.0, True)); res["ours_bwd_ms"] = t
+t, (o_r, l_r, _) = best(lambda: refk.forward(qn, kn, v, None, None, False, 8.0, True)); res["ref_fwd_ms"] = t
+res["max_abs_o_diff"] = float((o_r.float() - o_o.float()).abs().max())
+print("RESULT " + json.dumps(res), flush=True)
+if what == "bwd":
+    t, g_r = best(lambda: refk.backward(do, o_r, l_r, qn, kn, v, None, None, False, 8.0, True)); res["ref_bwd_ms"] = t
+    res["grad_rel_diff"] = [float((a.float() - b.float()).abs().max() / b.float().abs().max()) for a, b in zip(g_r[:3], g_o[:3])]
+    print("RESULT " + json.dumps(res), flush=True)
+"""
+
+
 def time_reference_cuda_kernel(out):
     """The reference's own .cu (wmma / scalar-FMA kernels, compiled for sm_100a) at (4,8,4096,64) f16 causal,
-    next to this repository's kernels - same tensors, CUDA events, best of 10."""
-    import torch
-    cand = [f for f in os.listdir(os.path.join(ROOT, "oracle", "_ref"))
-            if f.startswith("flash_cosine_sim_attention_cuda_ref") and f.endswith(".so")] if os.path.isdir(
-        os.path.join(ROOT, "oracle", "_ref")) else []
+    next to this repository's kernels - same tensors, CUDA events, best of 10.  Run in a child process: a fault
+    inside the reference's kernel must not take the runner down."""
+    import json
+    d = os.path.join(ROOT, "oracle", "_ref")
+    cand = [f for f in os.listdir(d) if f.startswith("flash_cosine_sim_attention_cuda_ref") and f.endswith(".so")] \
+        if os.path.isdir(d) else []
     log = os.path.join(out, "ref_cuda_kernel.log")
     if not cand:
         open(log, "w").write("oracle/_ref/flash_cosine_sim_attention_cuda_ref*.so not present (run oracle/stage_reference.py --cuda)\n")
         print("reference CUDA kernel: not built", flush=True)
         return
-    spec = importlib.util.spec_from_file_location("flash_cosine_sim_attention_cuda_ref",
-                                                  os.path.join(ROOT, "oracle", "_ref", cand[0]))
-    refk = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(refk)
-    sys.path.insert(0, ROOT)
-    import flash_cosine_sim_attention_b200 as ours
-    from flash_cosine_sim_attention_b200.flash_cosine_sim_attention import backward as our_bwd, forward as our_fwd
-    B, H, N, D = 4, 8, 4096, 64
-    dt = torch.float16
-    g = torch.Generator(device="cuda").manual_seed(0)
-    q, k, v, do = (torch.randn(B, H, N, D, generator=g, device="cuda", dtype=dt) for _ in range(4))
-    qn, kn = ours.l2norm_tensors(q, k)
-    flops_f, flops_b = 4 * B * H * N * N * D / 2, 10 * B * H * N * N * D / 2
-
-    def best(fn, n=10):
-        ts = []
-        for _ in range(n + 2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return min(ts[2:]), r
-    rows = []
-    t, (o_r, l_r, _) = best(lambda: refk.forward(qn, kn, v, None, None, False, 8.0, True))
-    rows.append(("reference forward_kernel (wmma)", t, flops_f))
-    t2, grads_r = best(lambda: refk.backward(do, o_r, l_r, qn, kn, v, None, None, False, 8.0, True))
-    rows.append(("reference backward (preprocess + backward_kernel + casts)", t2, flops_b))
-    t3, (o_o, l_o, _) = best(lambda: our_fwd(qn, kn, v, None, None, False, 8.0, True))
-    rows.append(("this repo fcsa_fwd_kernel (tcgen05)", t3, flops_f))
-    t4, grads_o = best(lambda: our_bwd(do, o_o, l_o, qn, kn, v, None, None, False, 8.0, True))
-    rows.append(("this repo backward (prep + fcsa_bwd_kernel + dq conversion)", t4, flops_b))
-    err_o = float((o_r.float() - o_o.float()).abs().max())
-    err_g = [float((a.float() - b.float()).abs().max() / b.float().abs().max()) for a, b in zip(grads_r[:3], grads_o[:3])]
+    res, notes = {}, []
+    for what in ("bwd", "fwd"):
+        p = subprocess.run([sys.executable, "-c", REFK_CHILD, ROOT, os.path.join(d, cand[0]), what], capture_output=True,
+                           text=True, timeout=600)
+        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")]
+        if lines:
+            res.update(json.loads(lines[-1][7:]))
+        if p.returncode != 0:
+            err = [ln for ln in (p.stdout + p.stderr).splitlines() if "rror" in ln]
+            notes.append(f"child '{what}' exited with {p.returncode}: " + (err[0][:200] if err else "no message"))
+        if "ref_bwd_ms" in res or what == "fwd":
+            break
+    ff, fb = 4 * 4 * 8 * 4096 * 4096 * 64 / 2, 10 * 4 * 8 * 4096 * 4096 * 64 / 2
     with open(log, "w") as f:
         f.write("(B,H,N,D) = (4,8,4096,64) float16 causal, already-normalised q, k; CUDA events, best of 10, one B200\n")
-        for name, ms, fl in rows:
-            line = f"{name:62s} {ms * 1e3:9.1f} us  {fl / (ms * 1e-3) / 1e12:8.1f} TFLOP/s"
+        for name, key, fl in (("reference forward_kernel (wmma, compiled for sm_100a)", "ref_fwd_ms", ff),
+                              ("reference backward (preprocess + backward_kernel + casts)", "ref_bwd_ms", fb),
+                              ("this repo forward (fcsa_fwd_kernel, tcgen05)", "ours_fwd_ms", ff),
+                              ("this repo backward (prep + fcsa_bwd_kernel + dq conversion)", "ours_bwd_ms", fb)):
+            if key in res:
+                line = f"{name:62s} {res[key] * 1e3:9.1f} us  {fl / (res[key] * 1e-3) / 1e12:8.1f} TFLOP/s"
+            else:
+                line = f"{name:62s}   did not complete"
             f.write(line + "\n")
             print("   " + line, flush=True)
-        f.write(f"speed-up forward {rows[0][1] / rows[2][1]:.1f}x, backward {rows[1][1] / rows[3][1]:.1f}x\n")
-        f.write(f"max |o_ref - o_ours| = {err_o:.3e}; relative-to-max differences of dq, dk, dv = {err_g}\n")
-    print(f"reference CUDA kernel vs ours: fwd {rows[0][1] / rows[2][1]:.1f}x, bwd {rows[1][1] / rows[3][1]:.1f}x; "
-          f"max|do| {err_o:.2e}, grads rel {['%.2e' % x for x in err_g]}", flush=True)
+        if "ref_fwd_ms" in res:
+            f.write(f"forward speed-up {res['ref_fwd_ms'] / res['ours_fwd_ms']:.1f}x; max |o_ref - o_ours| = {res.get('max_abs_o_diff')}\n")
+        if "ref_bwd_ms" in res:
+            f.write(f"backward speed-up {res['ref_bwd_ms'] / res['ours_bwd_ms']:.1f}x; relative-to-max differences of dq, dk, dv = {res.get('grad_rel_diff')}\n")
+        for n in notes:
+            f.write(n + "\n")
+            print("   note:", n, flush=True)
 
 
 def main():

@@ -105,3 +105,25 @@ def test_tma_ready_copies_only_when_needed():
     assert f(e).is_contiguous() and f(e) is not e
     t = torch.empty(2, 8, 10, 128, dtype=torch.float16)[..., ::2]
     assert f(t).stride(-1) == 1
+
+
+def test_extension_error_path_raises_runtime_error():
+    """A C-ABI error must surface as a Python RuntimeError carrying the library's message (the module once
+    crashed while unwinding: built with a toolchain whose exception tables did not match libtorch's)."""
+    from flash_cosine_sim_attention_b200.flash_cosine_sim_attention import _ext
+    with pytest.raises(RuntimeError, match="null problem"):
+        _ext()._error_path_selftest()
+
+
+def test_extension_module_has_the_reference_surface():
+    """forward / backward / debug under the reference's module name (cu:1928-1933, version.py:3)."""
+    import importlib
+    from flash_cosine_sim_attention_b200.flash_cosine_sim_attention import _ext
+    from flash_cosine_sim_attention_b200.version import __cuda_pkg_name__
+    m = _ext()
+    assert __cuda_pkg_name__ == "flash_cosine_sim_attention_cuda_0_1_40"
+    assert importlib.import_module(__cuda_pkg_name__) is m
+    for name in ("forward", "backward", "debug"):
+        assert callable(getattr(m, name))
+    with pytest.raises(RuntimeError, match="CUDA tensors required"):
+        m.forward(torch.zeros(1, 2, 8, 64), torch.zeros(1, 2, 8, 64), torch.zeros(1, 2, 8, 64), None, None, False, 8.0, False)
