@@ -206,12 +206,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    saved_stdout_fd = None
     if world > 1:
-        # NCCL's INFO lines (version banner, "nranks N", NVLS/ring choice) go to stderr so the run can be
-        # checked for a real N-rank communicator; stdout stays one JSON line
+        # NCCL's INFO lines (version banner, "nranks N", NVLS/ring choice) must be visible so the run can be
+        # checked for a real N-rank communicator, but NCCL writes them to STDOUT and stdout has to stay one JSON
+        # line: file descriptor 1 points at stderr for the whole run (every rank); rank 0 restores it for the
+        # very last thing it does, printing the line.
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -479,9 +483,16 @@ def main():
             line["cpu_baseline"] = {"value": f / t / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": kind,
                                     "sample": "3 x (1,2,4096,64) f32 causal fwd+bwd (2/32 of the workload each), "
                                               f"naive path of {src}, {os.cpu_count()} logical cpus"}
-        print(json.dumps(line), flush=True)
+        final_line = json.dumps(line)
+    else:
+        final_line = None
     if world > 1:
         dist.destroy_process_group()
+    if final_line is not None:
+        sys.stdout.flush()
+        if saved_stdout_fd is not None:
+            os.dup2(saved_stdout_fd, 1)
+        print(final_line, flush=True)
 
 
 if __name__ == "__main__":

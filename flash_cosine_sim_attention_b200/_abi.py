@@ -59,6 +59,8 @@ class FcsaProblem(Structure):
         ("shift", c_float),
         ("key_mask", c_void_p),
         ("key_mask_stride", c_int64),
+        ("out_f32", c_int32),
+        ("reserved_", c_int32),
     ]
 
 

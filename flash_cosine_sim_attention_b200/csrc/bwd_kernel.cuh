@@ -143,6 +143,7 @@ struct PrepArgs {
   int bpb;                          // blocks per (batch, head): the grid is 1-D (no 65535 limit on batch*heads)
   float c2;                         // shift * log2e
   const float* shift_extra;         // optional device scalar: shift += max(*shift_extra, 0) (bias range guard)
+  int o_f32;                        // 1: o is float32 (strides in float32 elements)
   const void* o;  long long o_sb, o_sh, o_sn;
   const void* d_o; long long do_sb, do_sh, do_sn;
   const float* inv_l;               // (B, H, Nq)
@@ -187,11 +188,14 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
   const int tr = threadIdx.x % TPR;
   const int padded = a.nqt * QT;
   const float c2 = a.c2 + (a.shift_extra != nullptr ? fmaxf(__ldg(a.shift_extra), 0.f) * 1.4426950408889634f : 0.f);
-  const T* obase = reinterpret_cast<const T*>(a.o) + b * a.o_sb + h * a.o_sh + tr * 8;
+  const long long o_off = b * a.o_sb + h * a.o_sh + tr * 8;
+  const T* obase = reinterpret_cast<const T*>(a.o) + o_off;
+  const float* obase32 = reinterpret_cast<const float*>(a.o) + o_off;
   const T* dbase = reinterpret_cast<const T*>(a.d_o) + b * a.do_sb + h * a.do_sh + tr * 8;
   int row[2];
   bool in[2], valid[2];
   uint4 ro[2], rd[2];
+  float4 rof[2][2];                           // o as float32 (o_f32 problems): 8 features = two float4
   float il[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -199,16 +203,26 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const PrepArgs a) {
     in[u] = row[u] < padded;
     valid[u] = in[u] && row[u] < a.Nq;
     ro[u] = rd[u] = make_uint4(0, 0, 0, 0);
+    rof[u][0] = rof[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     il[u] = 1.f;
     if (valid[u]) {
-      ro[u] = ldg_stream128(obase + (long long)row[u] * a.o_sn);
+      if (a.o_f32) {
+        rof[u][0] = __ldg(reinterpret_cast<const float4*>(obase32 + (long long)row[u] * a.o_sn));
+        rof[u][1] = __ldg(reinterpret_cast<const float4*>(obase32 + (long long)row[u] * a.o_sn + 4));
+      } else {
+        ro[u] = ldg_stream128(obase + (long long)row[u] * a.o_sn);
+      }
       rd[u] = ldg_stream128(dbase + (long long)row[u] * a.do_sn);
       if (tr == 0) il[u] = __ldg(a.inv_l + (long long)bh * a.Nq + row[u]);
     }
   }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    const float2 a0 = unpack2<T>(ro[u].x), a1 = unpack2<T>(ro[u].y), a2 = unpack2<T>(ro[u].z), a3 = unpack2<T>(ro[u].w);
+    float2 a0 = unpack2<T>(ro[u].x), a1 = unpack2<T>(ro[u].y), a2 = unpack2<T>(ro[u].z), a3 = unpack2<T>(ro[u].w);
+    if (a.o_f32) {
+      a0 = make_float2(rof[u][0].x, rof[u][0].y); a1 = make_float2(rof[u][0].z, rof[u][0].w);
+      a2 = make_float2(rof[u][1].x, rof[u][1].y); a3 = make_float2(rof[u][1].z, rof[u][1].w);
+    }
     const float2 b0 = unpack2<T>(rd[u].x), b1 = unpack2<T>(rd[u].y), b2 = unpack2<T>(rd[u].z), b3 = unpack2<T>(rd[u].w);
     float dot = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y +
                 a3.x * b3.x + a3.y * b3.y;
@@ -265,6 +279,7 @@ struct BwdArgs {
   // index space ([.][.][Nq][Nk] planes, strides dbias_sb (0 = summed over the batch) / dbias_sh) or nullptr.
   const void* bias; long long bias_sb, bias_sh, bias_sn;
   float* dbias; long long dbias_sb, dbias_sh;
+  int out_f32;                      // 1: dq, dk, dv are float32 tensors (strides in float32 elements)
   // dq conversion pass (D = 64, bwd_dq_finish64_kernel): fp32 accumulator tile -> 16-bit dq (x scale,
   // optional l2norm backward w.r.t. the raw q), tile cleared
   void* dq; long long dq_sb, dq_sh, dq_sn;
@@ -367,7 +382,12 @@ __device__ __forceinline__ void finish_dq_tile64(const BwdArgs& a, int bh, int b
       }
     }
   }
-  if (ok) {
+  if (ok && a.out_f32) {
+    float* dst = reinterpret_cast<float*>(a.dq) + b * a.dq_sb + h * a.dq_sh + (long long)row_g * a.dq_sn + part * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+  } else if (ok) {
     T* dst = reinterpret_cast<T*>(a.dq) + b * a.dq_sb + h * a.dq_sh + (long long)row_g * a.dq_sn + part * 16;
     uint4 o0, o1;
     o0.x = pack2<T>(g[0], g[1]);   o0.y = pack2<T>(g[2], g[3]);   o0.z = pack2<T>(g[4], g[5]);   o0.w = pack2<T>(g[6], g[7]);
@@ -994,7 +1014,16 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
-      if (store_ok) {
+      if (store_ok && a.out_f32 && !shared_kv) {
+        float* base = (w == 0)
+            ? reinterpret_cast<float*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + (long long)key_g * a.dv_sn
+            : reinterpret_cast<float*>(a.dk) + b * a.dk_sb + hk * a.dk_sh + (long long)key_g * a.dk_sn;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          *reinterpret_cast<float4*>(base + c * 32 + v4 * 4) =
+              make_float4(__uint_as_float(acc[4 * v4 + 0]) * mul, __uint_as_float(acc[4 * v4 + 1]) * mul,
+                          __uint_as_float(acc[4 * v4 + 2]) * mul, __uint_as_float(acc[4 * v4 + 3]) * mul);
+      } else if (store_ok) {
         if (!shared_kv) {
           T* base = (w == 0)
               ? reinterpret_cast<T*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + (long long)key_g * a.dv_sn
@@ -1030,6 +1059,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 struct DqFinishArgs {
   int B, H, Nq, D, nqt;
   float scale;
+  int out_f32;                      // 1: dq is float32
   float* dq_acc;
   void* dq; long long sb, sh, sn;
   // when q_rnorm is set, dq is the gradient w.r.t. the RAW queries (l2norm backward applied here)
@@ -1124,7 +1154,11 @@ __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArg
       qraw = ldg_stream128(reinterpret_cast<const T*>(a.q_hat) + b * a.q_sb + h * a.q_sh + (long long)row * a.q_sn +
                            c8 * 8);
     finish_l2norm_bwd<T>(g, a, ok, qraw, b, h, ok ? row : 0, c8);
-    if (ok) {
+    if (ok && a.out_f32) {
+      float* dst = reinterpret_cast<float*>(a.dq) + b * a.sb + h * a.sh + (long long)row * a.sn + c8 * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(g[4], g[5], g[6], g[7]);
+    } else if (ok) {
       uint4 o4;
       o4.x = pack2<T>(g[0], g[1]);
       o4.y = pack2<T>(g[2], g[3]);
@@ -1137,7 +1171,7 @@ __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArg
 }
 
 struct KvFinishArgs {
-  int B, Nk, D;
+  int B, Nk, D, out_f32;
   const float* acc;                 // (B, Nk, D) fp32
   void* out; long long sb, sn;
 };
@@ -1154,6 +1188,12 @@ __global__ void __launch_bounds__(256) bwd_kv_finish_kernel(const KvFinishArgs a
   const float* src = a.acc + rowid * a.D + c8 * 8;
   const float4 lo = *reinterpret_cast<const float4*>(src);
   const float4 hi = *reinterpret_cast<const float4*>(src + 4);
+  if (a.out_f32) {
+    float* dst = reinterpret_cast<float*>(a.out) + b * a.sb + (long long)n * a.sn + c8 * 8;
+    *reinterpret_cast<float4*>(dst) = lo;
+    *reinterpret_cast<float4*>(dst + 4) = hi;
+    return;
+  }
   uint4 o4;
   o4.x = pack2<T>(lo.x, lo.y);
   o4.y = pack2<T>(lo.z, lo.w);
@@ -1173,6 +1213,7 @@ struct BwdHostArgs {
   const uint8_t* mask; long long mask_sb;
   fcsa_tensor q, k, v, o, d_o, dq, dk, dv;
   const float* inv_l;
+  bool out_f32 = false;             // o (read), dq, dk, dv (written) are float32
   void* workspace;                  // scratch
   void* zeroed;                     // zero on entry, zero again on exit (dq accumulator, tile counters)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;   // optional: recorded around the main kernel
@@ -1217,6 +1258,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     pa.B = h.B; pa.H = h.H; pa.Nq = h.Nq; pa.Nk = h.Nk; pa.D = D; pa.nqt = w.nqt; pa.QT = Cfg::QT; pa.causal = h.causal;
     pa.c2 = h.shift * log2e;
     pa.shift_extra = h.bias_amax;
+    pa.o_f32 = h.out_f32 ? 1 : 0;
     pa.o = h.o.ptr; pa.o_sb = h.o.sb; pa.o_sh = h.o.sh; pa.o_sn = h.o.sn;
     pa.d_o = h.d_o.ptr; pa.do_sb = h.d_o.sb; pa.do_sh = h.d_o.sh; pa.do_sn = h.d_o.sn;
     pa.inv_l = h.inv_l; pa.stats = stats;
@@ -1274,6 +1316,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     a.dq = h.dq.ptr; a.dq_sb = h.dq.sb; a.dq_sh = h.dq.sh; a.dq_sn = h.dq.sn;
     a.q_hat = h.q.ptr; a.q_sb = h.q.sb; a.q_sh = h.q.sh; a.q_sn = h.q.sn;
     a.q_rnorm = h.q_rnorm;
+    a.out_f32 = h.out_f32 ? 1 : 0;
     auto kern = fcsa_bwd_kernel<T, D, BIAS>;
     e = ensure_dynamic_smem<fcsa_bwd_kernel<T, D, BIAS>>(Cfg::kSmem);
     if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(bwd)"; *ce = e; return FCSA_ERR_CUDA; }
@@ -1290,7 +1333,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     fa.B = h.B; fa.H = h.H; fa.Nq = h.Nq; fa.D = D; fa.nqt = w.nqt; fa.scale = h.scale;
     fa.dq_acc = dq_acc; fa.dq = h.dq.ptr; fa.sb = h.dq.sb; fa.sh = h.dq.sh; fa.sn = h.dq.sn;
     fa.q_hat = h.q.ptr; fa.q_sb = h.q.sb; fa.q_sh = h.q.sh; fa.q_sn = h.q.sn;
-    fa.q_rnorm = h.q_rnorm; fa.G = h.groups;
+    fa.q_rnorm = h.q_rnorm; fa.G = h.groups; fa.out_f32 = h.out_f32 ? 1 : 0;
     const long long tiles = (long long)h.B * h.H * w.nqt;
     if (tiles > 0x7FFFFFFFLL) { *err = "problem too large for one launch"; return FCSA_ERR_INVALID; }
     if (h.ev_finish[0]) cudaEventRecord(h.ev_finish[0], stream);
@@ -1302,7 +1345,7 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     if (shared_kv) {
       for (int which = 0; which < 2; ++which) {
         KvFinishArgs ka;
-        ka.B = h.B; ka.Nk = h.Nk; ka.D = D;
+        ka.B = h.B; ka.Nk = h.Nk; ka.D = D; ka.out_f32 = h.out_f32 ? 1 : 0;
         ka.acc = dkv_acc + (which ? (size_t)h.B * h.Nk * D : 0);
         const fcsa_tensor& t = which ? h.dv : h.dk;
         ka.out = t.ptr; ka.sb = t.sb; ka.sn = t.sn;

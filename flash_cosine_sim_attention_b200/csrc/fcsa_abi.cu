@@ -127,6 +127,7 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
   a.o_sb = o->sb;
   a.o_sh = o->sh;
   a.o_sn = o->sn;
+  a.o_f32 = p->out_f32 ? 1 : 0;
   a.inv_l = inv_l;
   a.bias = BIAS ? bias->ptr : nullptr;
   a.bias_sb = BIAS ? bias->sb : 0;
@@ -289,6 +290,9 @@ static int backward_impl(const fcsa_problem* p, const fcsa_tensor* q, const fcsa
   h.mask = p->key_mask; h.mask_sb = p->key_mask_stride;
   h.q = *q; h.k = *k; h.v = *v; h.o = *o; h.d_o = *d_o; h.dq = *dq; h.dk = *dk; h.dv = *dv;
   h.inv_l = inv_l;
+  h.out_f32 = p->out_f32 != 0;
+  if (h.out_f32 && (q_rnorm || k_rnorm))
+    return fail(FCSA_ERR_UNSUPPORTED, "out_f32 with the fused l2norm backward is not implemented (normalise outside)");
   h.workspace = workspace;
   h.zeroed = zeroed;
   h.ev_start = g_ev[1][0];

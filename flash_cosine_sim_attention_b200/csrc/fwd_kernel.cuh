@@ -46,6 +46,7 @@ struct FwdArgs {
   long long mask_sb;
   void* o;
   long long o_sb, o_sh, o_sn;   // element strides of o (feature dim contiguous)
+  int o_f32;                    // 1: o is float32 (strides in float32 elements), else the operand type
   float* inv_l;                 // (B, H, Nq) fp32, contiguous
   // additive bias on the logits (reference py:312, cu:1168,1214): element type = q's, [b][h][i][j] with
   // element strides (bias_sb = 0 when the bias has no batch dimension); rows are 16-byte aligned and
@@ -409,8 +410,10 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     l += lbuf[(half ^ 1) * 128 + r];
     const float inv = 1.0f / fmaxf(l, 1e-37f);
     const bool row_ok = row_g < a.Nq;
-    T* orow = reinterpret_cast<T*>(a.o) + (long long)b * a.o_sb + (long long)h * a.o_sh +
-              (long long)row_g * a.o_sn;
+    const long long o_off = (long long)b * a.o_sb + (long long)h * a.o_sh + (long long)row_g * a.o_sn;
+    T* orow = reinterpret_cast<T*>(a.o) + o_off;
+    float* orow32 = reinterpret_cast<float*>(a.o) + o_off;
+    const bool o_f32 = a.o_f32 != 0;
     constexpr int CPH = D / 64;              // 32-column chunks of O per half
     if (nt > 0) {
       mbar_wait(BAR(O_FULL + t), 0);
@@ -421,7 +424,13 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t acc[32];
         tmem_ld_x32(tO + c * 32, acc);
         tmem_ld_wait();
-        if (row_ok) {
+        if (row_ok && o_f32) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(orow32 + c * 32 + v * 4) =
+                make_float4(__uint_as_float(acc[4 * v + 0]) * inv, __uint_as_float(acc[4 * v + 1]) * inv,
+                            __uint_as_float(acc[4 * v + 2]) * inv, __uint_as_float(acc[4 * v + 3]) * inv);
+        } else if (row_ok) {
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint4 w;
@@ -433,6 +442,10 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
+    } else if (row_ok && o_f32) {
+#pragma unroll
+      for (int v = 0; v < D / 8; ++v)
+        *reinterpret_cast<float4*>(orow32 + half * (D / 2) + v * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (row_ok) {
 #pragma unroll
       for (int v = 0; v < D / 16; ++v)

@@ -97,8 +97,10 @@ struct Shapes {
 };
 
 fcsa_problem make_problem(const Shapes& sh, const Tensor& q, double scale, double shift, bool causal,
-                          const optional<Tensor>& mask_u8) {
+                          const optional<Tensor>& mask_u8, bool out_f32 = false) {
   fcsa_problem p;
+  p.out_f32 = out_f32 ? 1 : 0;
+  p.reserved_ = 0;
   p.dtype = dtype_code(q);
   p.batch = (int32_t)sh.B; p.heads = (int32_t)sh.H; p.kv_heads = (int32_t)sh.kv_heads;
   p.seq_q = (int32_t)sh.Nq; p.seq_k = (int32_t)sh.Nk; p.head_dim = (int32_t)sh.D;
@@ -204,19 +206,20 @@ Tensor l2norm_backward(const Tensor& dy_in, const Tensor& y_in, const Tensor& rn
 //   l2norm_groups == 0: q, k are used as given (already normalised, or l2norm_qk=False)
 //   bias_prepared     : the tensor prep_bias() made (saved by the caller for the backward), optional
 //   bias_amax         : optional fp32 device scalar; the kernels add max(amax, 0) to `shift` (fp16 range)
+//   out_f32           : o is returned as float32 (fp32 accumulator, no rounding to 16 bit) - float32 callers
 // returns (o, inv_l, q_hat, k_hat, q_rnorm, k_rnorm) - the last four undefined when l2norm_groups == 0
 // ------------------------------------------------------------------------------------------------
 std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> forward_ex(
     const Tensor& q_in, const Tensor& k_in, const Tensor& v_in, const optional<Tensor>& mask,
     const optional<Tensor>& bias_prepared, bool bias_batch_dim, const optional<Tensor>& bias_amax, double scale,
-    double shift, bool causal, int64_t l2norm_groups, bool need_inv_l) {
+    double shift, bool causal, int64_t l2norm_groups, bool need_inv_l, bool out_f32) {
   const Shapes sh(q_in, k_in, v_in);
   TORCH_CHECK(!(causal && mask.has_value() && mask->defined()), "mask should not be supplied if causality is needed");
   const c10::cuda::CUDAGuard guard(q_in.device());
   const Tensor q = tma_ready(q_in), k = tma_ready(k_in), v = tma_ready(v_in);
   const optional<Tensor> mask_u8 = prep_mask(mask, sh);
-  const fcsa_problem p = make_problem(sh, q, scale, shift, causal, mask_u8);
-  Tensor o = at::empty(q.sizes(), q.options());
+  const fcsa_problem p = make_problem(sh, q, scale, shift, causal, mask_u8, out_f32);
+  Tensor o = at::empty(q.sizes(), out_f32 ? q.options().dtype(at::kFloat) : q.options());   // out_f32: no final rounding
   Tensor inv_l;
   if (need_inv_l) inv_l = at::empty({sh.B, sh.H, sh.Nq}, q.options().dtype(at::kFloat));
   float* inv_l_ptr = need_inv_l ? inv_l.data_ptr<float>() : nullptr;
@@ -256,7 +259,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> backward_ex(
     const Tensor& v_in, const optional<Tensor>& q_rnorm, const optional<Tensor>& k_rnorm,
     const optional<Tensor>& mask, const optional<Tensor>& bias_prepared, bool bias_batch_dim,
     const optional<Tensor>& bias_amax, bool bias_grad, const optional<Tensor>& bias_like, double scale, double shift,
-    bool causal, int64_t groups) {
+    bool causal, int64_t groups, bool out_f32) {
   const Shapes sh(q_in, k_in, v_in);
   const c10::cuda::CUDAGuard guard(q_in.device());
   const Tensor q = tma_ready(q_in), k = tma_ready(k_in), v = tma_ready(v_in), o = tma_ready(o_in),
@@ -264,10 +267,13 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> backward_ex(
   TORCH_CHECK(d_o.sizes() == q.sizes() && d_o.scalar_type() == q.scalar_type(),
               "d_out must have the shape and dtype of the queries");
   const optional<Tensor> mask_u8 = prep_mask(mask, sh);
-  const fcsa_problem p = make_problem(sh, q, scale, shift, causal, mask_u8);
-  Tensor dq = at::empty(q.sizes(), q.options());
-  Tensor dk = at::empty(k.sizes(), k.options());
-  Tensor dv = at::empty(v.sizes(), v.options());
+  const fcsa_problem p = make_problem(sh, q, scale, shift, causal, mask_u8, out_f32);
+  TORCH_CHECK(o.scalar_type() == (out_f32 ? at::kFloat : q.scalar_type()), "backward_ex: `o` must be ",
+              out_f32 ? "float32 (out_f32)" : "in the operand dtype");
+  const auto gopt = out_f32 ? q.options().dtype(at::kFloat) : q.options();     // out_f32: float32 gradients
+  Tensor dq = at::empty(q.sizes(), gopt);
+  Tensor dk = at::empty(k.sizes(), gopt);
+  Tensor dv = at::empty(v.sizes(), gopt);
   cudaStream_t stream = at::cuda::getCurrentCUDAStream().stream();
   const Workspaces ws = backward_workspaces(p, q, stream);
   const fcsa_tensor tq = view4(q), tk = view4(k), tv = view4(v), to = view4(o), tdo = view4(d_o), tdq = view4(dq),
@@ -320,7 +326,8 @@ std::tuple<Tensor, Tensor, bool> forward(const Tensor& q, const Tensor& k, const
       q.requires_grad() || k.requires_grad() || v.requires_grad() || (has_bias && attn_bias->requires_grad());
   optional<Tensor> bias_prepared;
   if (has_bias) bias_prepared = prep_bias(*attn_bias, sh, q.scalar_type(), attn_bias_batch_dim);
-  auto r = forward_ex(q, k, v, mask, bias_prepared, attn_bias_batch_dim, c10::nullopt, scale, scale, causal, 0, true);
+  auto r = forward_ex(q, k, v, mask, bias_prepared, attn_bias_batch_dim, c10::nullopt, scale, scale, causal, 0, true,
+                      false);
   return {std::get<0>(r), std::get<1>(r), should_backwards};
 }
 
@@ -334,7 +341,7 @@ std::tuple<Tensor, Tensor, Tensor, optional<Tensor>> backward(
   optional<Tensor> bias_prepared;
   if (has_bias) bias_prepared = prep_bias(*attn_bias, sh, q.scalar_type(), attn_bias_batch_dim);
   auto r = backward_ex(d_out, o, l, q, k, v, c10::nullopt, c10::nullopt, mask, bias_prepared, attn_bias_batch_dim,
-                       c10::nullopt, has_bias && attn_bias->requires_grad(), attn_bias, scale, scale, causal, 0);
+                       c10::nullopt, has_bias && attn_bias->requires_grad(), attn_bias, scale, scale, causal, 0, false);
   optional<Tensor> db;
   if (std::get<3>(r).defined()) db = std::get<3>(r);
   return {std::get<0>(r), std::get<1>(r), std::get<2>(r), db};

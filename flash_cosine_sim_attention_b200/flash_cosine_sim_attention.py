@@ -158,7 +158,7 @@ def forward(q, k, v, mask, attn_bias, attn_bias_batch_dim, scale, causal, shift=
     should_backwards = any(t.requires_grad for t in (q, k, v)) or (exists(attn_bias) and attn_bias.requires_grad)
     bias = ext.prepare_bias(q, k, v, attn_bias, bool(attn_bias_batch_dim)) if exists(attn_bias) else None
     o, inv_l = ext.forward_ex(q, k, v, mask, bias, bool(attn_bias_batch_dim) or q.ndim == 3, None, float(scale),
-                              float(shift), bool(causal), 0, True)[:2]
+                              float(shift), bool(causal), 0, True, False)[:2]
     return o, inv_l, should_backwards
 
 
@@ -172,7 +172,7 @@ def backward(d_out, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, sca
     dq, dk, dv, db = ext.backward_ex(d_out, o, inv_l, q, k, v, None, None, mask, bias,
                                      bool(attn_bias_batch_dim) or q.ndim == 3, None,
                                      exists(attn_bias) and attn_bias.requires_grad, attn_bias, float(scale),
-                                     float(shift), bool(causal), 0)
+                                     float(shift), bool(causal), 0, False)
     return dq, dk, dv, db
 
 
@@ -195,7 +195,7 @@ class FlashCosineSimAttention(Function):
         bias = ext.prepare_bias(q, k, v, attn_bias, batch_dim) if exists(attn_bias) else None
         sft = float(scale if shift is None else shift)
         o, inv_l = ext.forward_ex(q, k, v, mask, bias, batch_dim, bias_amax, float(scale), sft, bool(causal), 0,
-                                  should_backwards)[:2]
+                                  should_backwards, False)[:2]
         if not should_backwards:
             return o
         ctx.should_backwards = should_backwards
@@ -212,28 +212,33 @@ class FlashCosineSimAttention(Function):
         scale, causal, batch_dim, shift, bias_grad, bias_dtype = ctx.params
         like = torch.empty(0, dtype=bias_dtype, device=q.device) if bias_grad else None
         dq, dk, dv, db = _ext().backward_ex(do, o, inv_l, q, k, v, None, None, mask, bias, batch_dim, bias_amax,
-                                            bias_grad, like, scale, shift, causal, 0)
+                                            bias_grad, like, scale, shift, causal, 0, False)
         return dq, dk, dv, None, db, None, None, None, None, None
 
 
 flash_cosine_sim_attention_cuda = FlashCosineSimAttention.apply
 
 
+_FP16_GROUPED_RANGE = 10.0      # scale * groups up to which exp(scale * q.k) fits fp16's normal range, see below
+
+
 def _choose_shift(dtype, scale, groups, l2norm_qk):
     """Constant subtracted from the logits before exp (any constant gives the same attention;
     the reference hard-codes `scale`, cu:1216).  p = exp(logit - shift) is stored in 16 bit:
       bf16: shift = scale*groups - p <= 1 for every possible q.k (<= groups); bf16 has fp32's range.
-      fp16, groups == 1: q.k <= 1, so shift = scale - 15 ln 2 puts p in (0, 2^15]: the top of the
-            fp16 range instead of its subnormals.
-      fp16, groups > 1: exp(scale*q.k) spans e^(2*scale*groups) - more than fp16 can hold without a
-            row max.  Same choice as the reference (shift = scale); the kernels saturate p at
-            65504 instead of producing inf.  Use bf16 for grouped l2norm with large scale*groups."""
+      fp16: q.k lies in [-groups, groups], so exp(scale*q.k) spans e^(2*scale*groups).  fp16's NORMAL range
+            is 2^-14 .. 2^15 (e^20); shift = scale*groups - 15 ln 2 puts the largest possible p at 2^15 and, as
+            long as scale*groups <= 10, the smallest at 2^15 e^-20 > 2^-14: nothing under- or overflows.
+      fp16, scale*groups > 10: more range than fp16 has without a row max.  Same choice as the reference
+            (shift = scale); the kernels saturate p at 65504 instead of producing inf and tiny p flush to
+            zero - rows whose best match is poor lose precision.  Use bf16 (or float32 inputs, which switch
+            to the bf16 kernels by themselves) for grouped l2norm with a large scale*groups."""
     if not l2norm_qk:
         return float(scale)
     if dtype == torch.bfloat16:
         return float(scale * groups)
-    if groups == 1:
-        return float(scale) - 15.0 * math.log(2.0)
+    if scale * groups <= _FP16_GROUPED_RANGE:
+        return float(scale * groups) - 15.0 * math.log(2.0)
     return float(scale)
 
 
@@ -248,7 +253,7 @@ class _FusedCosineSimAttention(Function):
                  else _choose_shift(q.dtype, scale, groups, l2norm_qk))
         needs_grad = any(ctx.needs_input_grad[:3])
         o, inv_l, qn, kn, rq, rk = ext.forward_ex(q, k, v, mask, None, False, None, scale, shift, causal,
-                                                  groups if l2norm_qk else 0, needs_grad)
+                                                  groups if l2norm_qk else 0, needs_grad, False)
         if needs_grad:
             if not l2norm_qk:
                 qn, kn = q, k
@@ -261,7 +266,7 @@ class _FusedCosineSimAttention(Function):
         o, inv_l, qn, kn, v, mask, rq, rk = ctx.saved_tensors
         scale, shift, causal, groups, l2norm_qk = ctx.params
         dq, dk, dv, _ = _ext().backward_ex(do, o, inv_l, qn, kn, v, rq, rk, mask, None, False, None, False, None,
-                                           scale, shift, causal, groups if l2norm_qk else 0)
+                                           scale, shift, causal, groups if l2norm_qk else 0, False)
         return dq, dk, dv, None, None, None, None, None, None
 
 
@@ -358,64 +363,65 @@ def _pow2_scale(t, top_exp):
     return torch.exp2(torch.floor(torch.log2(amax)) + 1 - top_exp)
 
 
-class _GradScaleDown(Function):
-    """Identity forward.  Backward: divides the incoming fp32 gradient by a power of two that brings its
-    largest magnitude to ~2^10 (stored in `holder` for _GradScaleUp) before it is cast to fp16."""
+class _Float32OnHalfKernels(Function):
+    """float32 q_hat, k_hat (already normalised if wanted), v (+ bias) -> float32 o, on the 16-bit kernels:
+    operands are rounded to `half` (fp16: 11-bit significand, tf32's; bf16 when fp16's exponent range is too
+    small), v and the incoming gradient are brought to [1, 2) by an exact power-of-two scale chosen on the
+    device (the kernels form dP = dO V^T and dS = P (dP - delta) in the 16-bit range, so operands keep headroom),
+    accumulation is fp32 and the results are written as float32 straight from the accumulators (out_f32)."""
 
     @staticmethod
-    def forward(ctx, x, holder):
-        ctx.holder = holder
-        return x.view_as(x)
+    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim, shift, half, use_amax):
+        ext = _ext()
+        D = q.shape[-1]
+        sv = _pow2_scale(v, 1)
+        qh, kh, vh = q.to(half), k.to(half), (v / sv).to(half)
+        if D not in _KERNEL_HEAD_DIMS:          # head dims 16 / 32 / 96 (reference cu:84): zero-padded features
+            Dp = 64 if D < 64 else 128
+            qh, kh, vh = (torch.nn.functional.pad(t, (0, Dp - D)) for t in (qh, kh, vh))
+        batch_dim = bool(attn_bias_batch_dim) or q.ndim == 3
+        bias = amax = None
+        if exists(attn_bias):
+            bias = ext.prepare_bias(qh, kh, vh, attn_bias.detach().to(half), batch_dim)
+            if use_amax:
+                amax = attn_bias.detach().amax().float().reshape(1)
+        needs_grad = any(ctx.needs_input_grad[:3]) or (exists(attn_bias) and ctx.needs_input_grad[4])
+        o, inv_l = ext.forward_ex(qh, kh, vh, mask, bias, batch_dim, amax, scale, shift, causal, 0, needs_grad, True)[:2]
+        if needs_grad:
+            ctx.save_for_backward(o, inv_l, qh, kh, vh, mask, bias, amax, sv)
+            ctx.params = (scale, shift, causal, batch_dim, D, exists(attn_bias) and ctx.needs_input_grad[4])
+        return o[..., :D] * sv
 
     @staticmethod
     def backward(ctx, g):
-        s = _pow2_scale(g, 10)
-        ctx.holder.s = s
-        return g / s, None
-
-
-class _GradScaleUp(Function):
-    """Identity forward.  Backward: multiplies the (fp32-cast) gradient back by the scale _GradScaleDown chose."""
-
-    @staticmethod
-    def forward(ctx, x, holder):
-        ctx.holder = holder
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g * ctx.holder.s, None
-
-
-class _Holder:
-    s = None
+        o, inv_l, qh, kh, vh, mask, bias, amax, sv = ctx.saved_tensors
+        scale, shift, causal, batch_dim, D, bias_grad = ctx.params
+        g = g * sv                                            # d(o_kernel) ; o = o_kernel * sv
+        sg = _pow2_scale(g, 1)
+        gh = (g / sg).to(qh.dtype)
+        if gh.shape[-1] != qh.shape[-1]:
+            gh = torch.nn.functional.pad(gh, (0, qh.shape[-1] - gh.shape[-1]))
+        dq, dk, dv, db = _ext().backward_ex(gh, o, inv_l, qh, kh, vh, None, None, mask, bias, batch_dim, amax,
+                                            bias_grad, None, scale, shift, causal, 0, True)
+        dq, dk, dv = dq[..., :D] * sg, dk[..., :D] * sg, dv[..., :D] * (sg / sv)
+        return dq, dk, dv, None, (db * sg if bias_grad else None), None, None, None, None, None, None
 
 
 def _float32_on_half_kernels(q, k, v, mask, attn_bias, scale, groups, causal, l2norm_qk, attn_bias_batch_dim):
     D = q.shape[-1]
     assert D % groups == 0, "groups must divide the head dim"
-    h = torch.float16
+    # fp16 (11-bit significand, like tf32) whenever its exponent range holds exp(scale * q.k); bf16 (8 bits, fp32's
+    # range) for grouped l2norm with a large scale*groups and for un-normalised q, k
+    h = torch.float16 if (l2norm_qk and scale * groups <= _FP16_GROUPED_RANGE) else torch.bfloat16
+    if h == torch.bfloat16:
+        _warn_once("f32-bf16", "flash_cosine_sim_attention: float32 inputs with scale*groups > "
+                               f"{_FP16_GROUPED_RANGE:g} (or l2norm_qk=False) run on the bfloat16 kernels - fp16's "
+                               "exponent range cannot hold exp(scale*q.k) there; operands carry 8 significant bits")
     if l2norm_qk:
         q, k = _l2norm_torch(q, groups), _l2norm_torch(k, groups)           # fp32, differentiable
-    sv = _pow2_scale(v, 8)                                                   # |v / sv| < 256
-    holder = _Holder()
-    up = lambda t: _GradScaleUp.apply(t, holder)
-    qh, kh, vh = up(q).to(h), up(k).to(h), up(v / sv).to(h)
-    if D not in _KERNEL_HEAD_DIMS:
-        # head dims 16 / 32 / 96 (reference cu:84): zero-padded features, as for 16-bit inputs
-        Dp = 64 if D < 64 else 128
-        qh, kh, vh = (torch.nn.functional.pad(t, (0, Dp - D)) for t in (qh, kh, vh))
     shift = _choose_shift(h, scale, groups if l2norm_qk else 1, l2norm_qk)
-    if exists(attn_bias):
-        bias_h = up(attn_bias).to(h)
-        amax = attn_bias.detach().amax().float().reshape(1) if l2norm_qk else None
-        oh = FlashCosineSimAttention.apply(qh, kh, vh, mask, bias_h, float(scale), bool(causal),
-                                           bool(attn_bias_batch_dim), float(shift), amax)
-    else:
-        oh = _FusedCosineSimAttention.apply(qh, kh, vh, mask, float(scale), bool(causal), 1, False,
-                                            int(groups) if l2norm_qk else 0)
-    o = _GradScaleDown.apply(oh[..., :D].float(), holder)
-    return o * sv
+    return _Float32OnHalfKernels.apply(q, k, v, mask, attn_bias, float(scale), bool(causal), bool(attn_bias_batch_dim),
+                                       float(shift), h, bool(l2norm_qk and h == torch.float16))
 
 
 _warned = set()

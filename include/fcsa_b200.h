@@ -71,6 +71,11 @@ typedef struct fcsa_problem {
   float shift;       /* p = exp(logit - shift); the reference uses shift = scale (cu:1216)    */
   const uint8_t* key_mask;   /* (batch, seq_k) bytes, nonzero = attend; NULL = no mask (cu:1198-1212) */
   int64_t key_mask_stride;   /* bytes between batches                                         */
+  int32_t out_f32;   /* 0: o (forward; also the `o` the backward reads), dq, dk, dv have the problem dtype.
+                        1: they are float32 tensors (strides then count float32 elements) - the accumulators are
+                        fp32 anyway, this only skips the final rounding to 16 bit.  q, k, v, d_o stay 16-bit
+                        operands.  Used for float32 callers (reference: Float dispatch, cu:1702-1703)        */
+  int32_t reserved_;
 } fcsa_problem;
 
 /* Library / ABI version: major*10000 + minor*100 + patch. */

@@ -71,8 +71,7 @@ def run_tests(ref, out):
                 "    mod = request.module\n    orig = mod.allclose\n"
                 "    monkeypatch.setattr(mod, 'allclose', lambda a, b, atol=1e-4: orig(a, b, atol=max(atol, 1e-3)))\n")
     cmd2 = [sys.executable, "-m", "pytest", os.path.join(ref, "tests", "test.py"), "-q", "-p", "no:cacheprovider",
-            "-k", "not cpu", "--tb=line", "-c", "/dev/null", "--rootdir", out, "--confcutdir", out,
-            "-p", "fcsa_f32_tol_plugin"]
+            "-k", "not cpu", "--tb=line", "-p", "fcsa_f32_tol_plugin"]
     e2 = env()
     e2["PYTHONPATH"] = out + os.pathsep + e2["PYTHONPATH"]
     p2 = subprocess.run(cmd2, cwd=out, env=e2, capture_output=True, text=True, timeout=1500)
@@ -220,6 +219,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     ap.add_argument("--only", default="tests,benchmark,train,refkernel")
     args = ap.parse_args()
+    args.out = os.path.abspath(args.out)
     os.makedirs(args.out, exist_ok=True)
     ref = find_reference()
     if ref is None:

@@ -37,9 +37,10 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_struct_layouts():
-    # fcsa_tensor: void* + 3 x int64; fcsa_problem: 8 x int32, 2 x float, pointer, int64
+    # fcsa_tensor: void* + 3 x int64; fcsa_problem: 8 x int32, 2 x float, pointer, int64, 2 x int32
     assert ctypes.sizeof(_abi.FcsaTensor) == 32
-    assert ctypes.sizeof(_abi.FcsaProblem) == 8 * 4 + 2 * 4 + 8 + 8
+    assert ctypes.sizeof(_abi.FcsaProblem) == 8 * 4 + 2 * 4 + 8 + 8 + 8
+    assert _abi.FcsaProblem.out_f32.offset == 56
     assert _abi.FcsaProblem.key_mask.offset == 40
 
 
