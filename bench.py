@@ -190,6 +190,31 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this rank's host threads (and therefore its pinned staging buffers: first touch) to the NUMA node the
+    GPU hangs off.  Host<->device copies through the other socket ran at half the bandwidth on some boxes, and
+    eight ranks enqueueing from arbitrary cores was part of the N = 8 slowdown of round 1.  Best effort."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"node": None, "note": "kernel reports no NUMA affinity for the GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"node": node, "note": "no allowed cpu on that node"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as e:      # noqa: BLE001
+        return {"node": None, "note": f"not bound ({type(e).__name__})"}
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -225,6 +250,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load()
@@ -466,7 +492,7 @@ def main():
                                   "note": "instrumented second pass (events between the launches); the headline pass "
                                           "has none"},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
-            "host_enqueue_us_per_step": host_enqueue_us, "clocks": clocks,
+            "host_enqueue_us_per_step": host_enqueue_us, "numa": numa, "clocks": clocks,
             "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
             "slowest_step_index": int(max(range(len(step_ms)), key=lambda j: step_ms[j])),
         }
