@@ -253,6 +253,11 @@ def main():
     numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        probe = torch.ones(1, device=dev)
+        dist.all_reduce(probe)                   # creates the communicator now; every rank contributes 1
+        if rank == 0:
+            print(f"[bench] NCCL communicator up: nranks {world} (all_reduce of ones = {int(probe.item())}), "
+                  f"NCCL {'.'.join(map(str, torch.cuda.nccl.version()))}, one process per GPU", file=sys.stderr, flush=True)
     lib = _abi.load()
     W = max(args.warmup, 3)
     K = args.steps

@@ -1130,15 +1130,21 @@ __global__ void __launch_bounds__(256) bwd_dq_finish128_kernel(const DqFinishArg
   const int bh = (int)(unit / a.nqt);
   const int b = bh / a.H, h = bh % a.H;
   float* src = a.dq_acc + unit * 8192;
-  for (int f = threadIdx.x; f < 2048; f += 256) {         // 2048 float4 per tile
-    const float4 v = *reinterpret_cast<const float4*>(src + f * 4);
+  // 2048 float4 per tile = 8 per thread: all eight loads first (L2, the bulk reduce-adds have just produced the
+  // tile there), then the zeros - a store between two loads of the same array would serialise them
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ldg_cg128f(src + (threadIdx.x + 256 * i) * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = threadIdx.x + 256 * i;
     *reinterpret_cast<float4*>(src + f * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int wq = f >> 9, c = (f >> 5) & 15, ln = f & 31;
     const int d = wq * 32 + ln, r0 = c * 4;
-    tile[r0 + 0][d] = v.x;
-    tile[r0 + 1][d] = v.y;
-    tile[r0 + 2][d] = v.z;
-    tile[r0 + 3][d] = v.w;
+    tile[r0 + 0][d] = v[i].x;
+    tile[r0 + 1][d] = v[i].y;
+    tile[r0 + 2][d] = v[i].z;
+    tile[r0 + 3][d] = v[i].w;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 64 * 16; e += 256) {      // 16 x 8 features per row

@@ -387,6 +387,41 @@ def test_two_streams_have_their_own_workspaces(fcsa):
         assert rel_err(gq, ref[1]) <= TOL_GRAD[dt]
 
 
+def test_cuda_graph_capture_of_a_training_step(fcsa):
+    """The whole fwd+bwd (5 launches with programmatic dependent launch, persistent workspaces, no host
+    synchronisation anywhere) can be captured in a CUDA graph and replayed on new data - the launch-bound
+    regime of small problems (SURVEY par. 8f row 4: "persistent / graph-captured launch")."""
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(51)
+    shape = (2, 4, 384, 64)
+    sq, sk, sv, sdo = (torch.zeros(shape, dtype=dt, device="cuda") for _ in range(4))
+    sq.requires_grad_(), sk.requires_grad_(), sv.requires_grad_()
+
+    def step():
+        o = fcsa.flash_cosine_sim_attention(sq, sk, sv, causal=True)
+        return (o,) + torch.autograd.grad(o, (sq, sk, sv), sdo)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()                                         # warm-up: workspaces of this stream exist before capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        outs = step()
+    for trial in range(2):
+        q, k, v, do = (torch.randn(shape, generator=g).to(dt) for _ in range(4))
+        with torch.no_grad():
+            sq.copy_(q); sk.copy_(k); sv.copy_(v); sdo.copy_(do)
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = oracle.attention(q.float().numpy(), k.float().numpy(), v.float().numpy(), causal=True,
+                               d_out=do.float().numpy(), round_qk="bf16")
+        assert rel_err(outs[0], ref[0]) <= TOL_OUT[dt]
+        for got, want in zip(outs[1:], ref[1:]):
+            assert rel_err(got, want) <= TOL_GRAD[dt]
+
+
 def test_fully_masked_rows_give_zero(fcsa):
     """Documented divergence from the naive formulation (reference cu:1239): o = 0, grads = 0."""
     q, k, v, do, _ = make_inputs((2, 2, 70, 64), (2, 2, 90, 64), torch.bfloat16, 12)
