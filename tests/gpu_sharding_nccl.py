@@ -5,6 +5,8 @@ Run on a multi-GPU box:
 Checks, on every rank, against the unsharded fused operator computed locally:
   * batch split + gather=True: the all-gathered output and the gradients of the local shard
   * heads split with single-head keys/values: dk, dv summed over ranks by the all-reduce in the backward
+  * context parallelism (the sequence split over the ranks): all-gather of k, v, one fused forward / backward per key
+    block, additive merge, reduce-scatter of dk, dv - against the unsharded fused operator on the whole sequence
 (The CPU/gloo version of the same logic with the plain operator is tests/test_sharding.py.)"""
 import os
 import sys
@@ -67,6 +69,27 @@ def main():
     worst = max(worst, *e)
     # dk, dv: sum over ranks of per-rank 16-bit partial results vs one fp32 accumulation over all heads
     assert e[0] < 1e-6 and e[1] < 1e-6 and e[2] < 2e-2 and e[3] < 2e-2, f"heads split: {e}"
+
+    # ---- 3. context (sequence) parallelism: one sequence split over the ranks, fused kernels per key block ---------
+    from flash_cosine_sim_attention_b200.context_parallel import context_parallel_cosine_sim_attention
+    cp_worst = 0.0
+    for causal in (True, False):
+        B, H, n, D = 2, 4, 384, 64
+        N = n * world
+        q, k, v, do = (torch.randn(B, H, N, D, generator=g).to(dt).to(dev) for _ in range(4))
+        qf, kf, vf = (t.clone().requires_grad_() for t in (q, k, v))
+        of = flash_cosine_sim_attention(qf, kf, vf, causal=causal)
+        of.backward(do)
+        sl = slice(rank * n, (rank + 1) * n)
+        ql, kl, vl = (t[:, :, sl].clone().requires_grad_() for t in (q, k, v))
+        o = context_parallel_cosine_sim_attention(ql, kl, vl, causal=causal)
+        o.backward(do[:, :, sl].contiguous())
+        e = [relerr(o, of[:, :, sl]), relerr(ql.grad, qf.grad[:, :, sl]), relerr(kl.grad, kf.grad[:, :, sl]),
+             relerr(vl.grad, vf.grad[:, :, sl])]
+        cp_worst = max(cp_worst, *e)
+        # two roundings apart: per-block 16-bit P / dS vs the single-pass kernel; same operands, fp32 merges
+        assert max(e) < 2e-2, f"context parallel (causal={causal}): {e}"
+    worst = max(worst, cp_worst)
 
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -613,6 +613,46 @@ def test_config3_causal_4x8x4096x64_fwd_bwd(fcsa, dtype):
     assert torch.equal(o3[:, :, :-1], o.detach()[:, :, :-1])
 
 
+def _f64_attention_on_gpu(q, k, v, do, scale=8.0):
+    """The oracle formula (py:75-126) for ONE (batch, head), causal, evaluated in float64 on the GPU with autograd;
+    q, k are l2-normalised in float64 and rounded to the input dtype first, as py:64 does.  Test infrastructure."""
+    dt = q.dtype
+    q64, k64, v64 = (t.double().detach().requires_grad_() for t in (q, k, v))
+    qn = torch.nn.functional.normalize(q64, dim=-1)
+    kn = torch.nn.functional.normalize(k64, dim=-1)
+    qn = qn + (qn.to(dt).double() - qn).detach()          # value rounded to the storage dtype, gradient straight through
+    kn = kn + (kn.to(dt).double() - kn).detach()
+    sim = (qn @ kn.t()) * scale
+    n = sim.shape[0]
+    sim = sim.masked_fill(torch.ones(n, n, dtype=torch.bool, device=q.device).triu(1), float("-inf"))
+    o = sim.softmax(dim=-1) @ v64
+    o.backward(do.double())
+    return o.detach(), q64.grad, k64.grad, v64.grad
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_config3_every_batch_head_against_float64_on_gpu(fcsa, dtype):
+    """ALL 32 (batch, head) problems of the metric configuration, outputs and the three gradients, against a float64
+    evaluation of the oracle formula on the same GPU (the numpy oracle checks two of them in
+    test_config3_causal_4x8x4096x64_fwd_bwd; 32 x 4096^2 float64 similarity matrices are too slow on the host)."""
+    g = torch.Generator(device="cuda").manual_seed(33)
+    q, k, v, do = (torch.randn(4, 8, 4096, 64, generator=g, device="cuda").to(dtype) for _ in range(4))
+    qd, kd, vd = (t.clone().requires_grad_() for t in (q, k, v))
+    o = fcsa.flash_cosine_sim_attention(qd, kd, vd, causal=True)
+    o.backward(do)
+    worst = {"o": 0.0, "dq": 0.0, "dk": 0.0, "dv": 0.0}
+    for b in range(4):
+        for h in range(8):
+            ref = _f64_attention_on_gpu(q[b, h], k[b, h], v[b, h], do[b, h])
+            for name, got, want in zip(worst, (o[b, h], qd.grad[b, h], kd.grad[b, h], vd.grad[b, h]), ref):
+                err = float((got.double() - want).abs().max() / want.abs().max())
+                worst[name] = max(worst[name], err)
+    for name, err in worst.items():
+        tol = TOL_OUT[dtype] if name == "o" else TOL_GRAD[dtype]
+        record(dtype, f"{name}@C3x32", err, tol)
+        assert err <= tol, (name, err)
+
+
 def test_config5_long_context_slice_16384x128(fcsa):
     """One rank's share of config 5 is (1, 16, 16384, 128); two heads checked against the oracle."""
     _slice_check(fcsa, (1, 2, 16384, 128), torch.bfloat16, [(0, 1)], grads=True)

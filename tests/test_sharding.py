@@ -88,3 +88,43 @@ def test_sharded_equals_unsharded_world2(case):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, case, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)), dict(out)
+
+
+# ---- context (sequence) parallelism: one long sequence split over the ranks -----------------------------------
+def _cp_worker(rank, world, port, causal, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flash_cosine_sim_attention_b200.context_parallel import (TorchPrimitives,
+                                                                      context_parallel_cosine_sim_attention)
+        g = torch.Generator().manual_seed(3)
+        B, H, N, D = 2, 3, 24, 16                                   # N split in `world` blocks of 12
+        q, k, v, do = (torch.randn(B, H, N, D, generator=g, dtype=torch.float64) for _ in range(4))
+        n = N // world
+        sl = slice(rank * n, (rank + 1) * n)
+        ql, kl, vl = (t[:, :, sl].clone().requires_grad_() for t in (q, k, v))
+        prims = TorchPrimitives(scale=8.0, shift=8.0)
+        o = context_parallel_cosine_sim_attention(ql, kl, vl, causal=causal, primitives=prims)
+        (o * do[:, :, sl]).sum().backward()
+        q2, k2, v2 = (t.clone().requires_grad_() for t in (q, k, v))
+        ref = plain_cosine_sim_attention(q2, k2, v2, causal=causal)
+        (ref * do).sum().backward()
+        ok = torch.allclose(o, ref[:, :, sl], atol=1e-12)
+        for got, want in ((ql.grad, q2.grad), (kl.grad, k2.grad), (vl.grad, v2.grad)):
+            ok = ok and torch.allclose(got, want[:, :, sl], atol=1e-10)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_context_parallel_equals_unsharded_world2(causal):
+    """Sequence split over 2 ranks: all-gather of k, v; per-block partial results merged additively (no running
+    max); dk, dv returned to their owners by a reduce-scatter.  Outputs and all three gradients of every rank's
+    block equal the unsharded naive attention."""
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_cp_worker, args=(world, _free_port(), causal, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world)), dict(out)
