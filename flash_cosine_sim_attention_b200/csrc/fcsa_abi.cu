@@ -364,8 +364,8 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
     if (a.N > max_rows) max_rows = a.N;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  constexpr int U = 2;                                       // rows per thread
-  const int rows_per_block = U * (256 / (p->head_dim / 8));
+  constexpr int U = 2;                                       // rows per thread (16 features each)
+  const int rows_per_block = U * (256 / (p->head_dim / 16));
   const long long bhs = (long long)pa.t[0].B * pa.t[0].H + (long long)pa.t[1].B * pa.t[1].H;
   if (bhs > 65535) {
     // more (batch, head) pairs than grid.y holds (merged batch-heads layouts): one 1-D-grid launch per tensor
@@ -379,11 +379,11 @@ int fcsa_forward_fused(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_t
   const bool bf = p->dtype == FCSA_BF16;
   if (g_ev[2][0]) cudaEventRecord(g_ev[2][0], s);
   if (p->head_dim == 64)
+    e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 4, U>, grid, dim3(256), 0, s, pa)
+           : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 4, U>, grid, dim3(256), 0, s, pa);
+  else if (p->head_dim == 128)
     e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 8, U>, grid, dim3(256), 0, s, pa)
            : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 8, U>, grid, dim3(256), 0, s, pa);
-  else if (p->head_dim == 128)
-    e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 16, U>, grid, dim3(256), 0, s, pa)
-           : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 16, U>, grid, dim3(256), 0, s, pa);
   else
     e = bf ? fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__nv_bfloat16, 0, U>, grid, dim3(256), 0, s, pa)
            : fcsa::launch_pdl(fcsa::l2norm_fwd_pair_kernel<__half, 0, U>, grid, dim3(256), 0, s, pa);

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const L2Args a) {
 }
 
 // q and k in one launch.  grid = (row blocks, batch*heads of q + batch*heads of k): blockIdx.y selects the
-// tensor and its (batch, head), so no thread divides 64-bit indices; one thread owns 8 features of U rows
-// and issues its U 16-byte loads before the first reduction.  TPR = threads per row (D / 8) when known at
-// compile time (8 or 16), 0 = read it from the arguments.  A short-lived-CTA grid (many waves of small CTAs,
+// tensor and its (batch, head), so no thread divides 64-bit indices; one thread owns 16 features of U rows
+// and issues its 2 U 16-byte loads before the first reduction.  TPR = threads per row (D / 16) when known at
+// compile time (4 or 8), 0 = read it from the arguments (head dims 32 and 256: D must be a multiple of 16).  A short-lived-CTA grid (many waves of small CTAs,
 // 8 resident per SM) measured faster here than a persistent loop: the per-item bookkeeping of the loop
 // (item decode with 64-bit divisions, register copies of the prefetched rows) cost more instructions than the
 // rows themselves (profiles/r02_aux_kernels.txt).
@@ -117,27 +117,33 @@ struct L2PairArgs {
 
 template <typename T, int TPR, int U>
 __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs pa) {
+  // TPR threads per row, SIXTEEN features per thread (two 16-byte loads): the pass is issue-bound before it is
+  // memory-bound (ncu: 84 % issue-slot utilisation with 8 features per thread), so the per-row bookkeeping
+  // (addresses, shuffle steps, predicates) is spread over twice the bytes.
   pdl_launch_dependents();
   pdl_wait();
   const int bh0 = pa.t[0].B * pa.t[0].H;
   const int which = blockIdx.y >= bh0;
   const L2Args& a = pa.t[which];
   const int bh = blockIdx.y - (which ? bh0 : 0);
-  const int tpr = TPR ? TPR : (a.D >> 3);
+  const int tpr = TPR ? TPR : (a.D >> 4);
   const int rpp = 256 / tpr;                          // rows per pass
   const int tr = threadIdx.x % tpr;
   const int r_in = threadIdx.x / tpr;
   const int row0 = blockIdx.x * (U * rpp);
   if (row0 >= a.N) return;                            // the grid is sized for the longer of the two tensors
   const int b = bh / a.H, h = bh - b * a.H;
-  const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 8;
-  T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 8;
-  uint4 raw[U];
+  const T* xbase = reinterpret_cast<const T*>(a.x) + b * a.x_sb + h * a.x_sh + tr * 16;
+  T* ybase = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + tr * 16;
+  uint4 raw[U][2];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int n = row0 + u * rpp + r_in;
-    raw[u] = make_uint4(0, 0, 0, 0);
-    if (n < a.N) raw[u] = ldg_stream128(xbase + (long long)n * a.x_sn);
+    raw[u][0] = raw[u][1] = make_uint4(0, 0, 0, 0);
+    if (n < a.N) {
+      raw[u][0] = ldg_stream128(xbase + (long long)n * a.x_sn);
+      raw[u][1] = ldg_stream128(xbase + (long long)n * a.x_sn + 8);
+    }
   }
   const int gs = a.D / a.G;
 #pragma unroll
@@ -145,40 +151,60 @@ __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs p
     const int n = row0 + u * rpp + r_in;
     const bool ok = n < a.N;
     const long long row = (long long)bh * a.N + n;
-    float f[8];
-    {
-      float2 t0 = unpack2<T>(raw[u].x), t1 = unpack2<T>(raw[u].y), t2 = unpack2<T>(raw[u].z), t3 = unpack2<T>(raw[u].w);
-      f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y; f[4] = t2.x; f[5] = t2.y; f[6] = t3.x; f[7] = t3.y;
+    float f[16];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const float2 t0 = unpack2<T>(raw[u][s2].x), t1 = unpack2<T>(raw[u][s2].y), t2 = unpack2<T>(raw[u][s2].z),
+                   t3 = unpack2<T>(raw[u][s2].w);
+      f[8 * s2] = t0.x; f[8 * s2 + 1] = t0.y; f[8 * s2 + 2] = t1.x; f[8 * s2 + 3] = t1.y;
+      f[8 * s2 + 4] = t2.x; f[8 * s2 + 5] = t2.y; f[8 * s2 + 6] = t3.x; f[8 * s2 + 7] = t3.y;
     }
-    float rn[8];
-    if (gs >= 8) {
+    float rn[16];
+    if (gs >= 16) {
       float ss = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-      const int tpg = gs >> 3;
+      for (int i = 0; i < 16; ++i) ss += f[i] * f[i];
+      const int tpg = gs >> 4;                         // threads per group
       ss = group_reduce(ss, tpg);
       const float r = rnorm_of(ss);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rn[i] = r;
+      for (int i = 0; i < 16; ++i) rn[i] = r;
       if (ok && a.rnorm && (tr & (tpg - 1)) == 0) a.rnorm[row * a.G + tr / tpg] = r;
+    } else if (gs == 8) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += f[8 * s2 + i] * f[8 * s2 + i];
+        const float r = rnorm_of(ss);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rn[8 * s2 + i] = r;
+        if (ok && a.rnorm) a.rnorm[row * a.G + 2 * tr + s2] = r;
+      }
     } else {
-      float sq[8], ss[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sq[i] = f[i] * f[i];
-      subgroup_sums8(sq, gs, ss);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        float sq[8], ss[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rn[i] = rnorm_of(ss[i]);
-        if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = rn[i];
+        for (int i = 0; i < 8; ++i) sq[i] = f[8 * s2 + i] * f[8 * s2 + i];
+        subgroup_sums8(sq, gs, ss);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rn[8 * s2 + i] = rnorm_of(ss[i]);
+          if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 16 + 8 * s2 + i) / gs] = rn[8 * s2 + i];
+        }
       }
     }
     if (ok) {
-      uint4 wv;
-      wv.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
-      wv.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
-      wv.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
-      wv.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
-      *reinterpret_cast<uint4*>(ybase + (long long)n * a.y_sn) = wv;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        uint4 wv;
+        wv.x = pack2<T>(f[8 * s2 + 0] * rn[8 * s2 + 0], f[8 * s2 + 1] * rn[8 * s2 + 1]);
+        wv.y = pack2<T>(f[8 * s2 + 2] * rn[8 * s2 + 2], f[8 * s2 + 3] * rn[8 * s2 + 3]);
+        wv.z = pack2<T>(f[8 * s2 + 4] * rn[8 * s2 + 4], f[8 * s2 + 5] * rn[8 * s2 + 5]);
+        wv.w = pack2<T>(f[8 * s2 + 6] * rn[8 * s2 + 6], f[8 * s2 + 7] * rn[8 * s2 + 7]);
+        *reinterpret_cast<uint4*>(ybase + (long long)n * a.y_sn + 8 * s2) = wv;
+      }
     }
   }
 }

@@ -48,9 +48,9 @@ int main() {
     a.x = t ? k : q; a.y = t ? kn : qn; a.rnorm = t ? rk : rq;
   }
   {
-    dim3 grid((N + 63) / 64, 2 * B * H);
-    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 2><<<grid, 256>>>(pa); }, 4.0 * n * 2);
-    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 8, 2><<<grid, 256>>>(pa); }, 4.0 * n * 2, false);
+    dim3 grid((N + 127) / 128, 2 * B * H);
+    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 4, 2><<<grid, 256>>>(pa); }, 4.0 * n * 2);
+    time_it("l2norm_fwd_pair", [&] { fcsa::l2norm_fwd_pair_kernel<bf16, 4, 2><<<grid, 256>>>(pa); }, 4.0 * n * 2, false);
   }
   // prep (per-row constants + slivers; no accumulator zeroing any more)
   {
