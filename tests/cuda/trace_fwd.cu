@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DFCSA_TRACE -o trace_fwd trace_fwd.cu
 // Test infrastructure only.
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 
 #include "../../flash_cosine_sim_attention_b200/csrc/fwd_kernel.cuh"
@@ -38,6 +39,7 @@ int main(int argc, char** argv) {
       fcsa::make_tensor_map_bhnd(&tk, k, true, B, H, Nk, D, sb, sh, sn, 128) ||
       fcsa::make_tensor_map_bhnd(&tv, v, true, B, H, Nk, D, sb, sh, sn, 128)) { printf("tmap fail\n"); return 1; }
   fcsa::FwdArgs a;
+  memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.causal = causal; a.has_mask = 0; a.kv_heads = H; a.n_qblk = (Nq + 255) / 256;
   a.c1 = 8.f * 1.44269504f; a.c2 = a.c1; a.mask = nullptr; a.mask_sb = 0;
   a.o = o; a.o_sb = sb; a.o_sh = sh; a.o_sn = sn; a.inv_l = inv_l;
