@@ -19,6 +19,9 @@ CONFIGS = [
     ("C5 per-GPU share (1,16,16384,128) bf16 causal fwd+bwd", (1, 16, 16384, 128), (1, 16, 16384, 128), torch.bfloat16, dict(causal=True), True),
     ("(4,8,8192,64) bf16 causal fwd+bwd", (4, 8, 8192, 64), (4, 8, 8192, 64), torch.bfloat16, dict(causal=True), True),
     ("(4,8,4096,128) bf16 causal fwd+bwd", (4, 8, 4096, 128), (4, 8, 4096, 128), torch.bfloat16, dict(causal=True), True),
+    ("C3 + attn_bias (8,4096,4096) no bias grad, bf16 causal fwd+bwd", (4, 8, 4096, 64), (4, 8, 4096, 64), torch.bfloat16, dict(causal=True, bias="nograd"), True),
+    ("C3 + attn_bias (8,4096,4096) with d_bias, bf16 causal fwd+bwd", (4, 8, 4096, 64), (4, 8, 4096, 64), torch.bfloat16, dict(causal=True, bias="grad"), True),
+    ("C3 float32 inputs (fp16 kernels), causal fwd+bwd", (4, 8, 4096, 64), (4, 8, 4096, 64), torch.float32, dict(causal=True), True),
 ]
 
 
@@ -31,6 +34,12 @@ def main():
         k = torch.randn(kvs, generator=g).to(dt).to(dev).requires_grad_(bwd)
         v = torch.randn(kvs, generator=g).to(dt).to(dev).requires_grad_(bwd)
         do = torch.randn(qs, generator=g).to(dt).to(dev)
+        kw = dict(kw)
+        bias_mode = kw.pop("bias", None)
+        bias = None
+        if bias_mode:
+            bias = (torch.randn(qs[1], qs[2], kvs[-2], generator=g) * 0.5).to(dt).to(dev).requires_grad_(bias_mode == "grad")
+            kw["attn_bias"] = bias
         mask = None
         if "mask" in name:
             mask = torch.rand(qs[0], kvs[-2], generator=g).to(dev) > 0.25
@@ -38,7 +47,7 @@ def main():
         def step():
             o = flash_cosine_sim_attention(q, k, v, mask=mask, **kw)
             if bwd:
-                torch.autograd.grad(o, (q, k, v), do)
+                torch.autograd.grad(o, (q, k, v) + ((bias,) if bias is not None and bias.requires_grad else ()), do)
 
         for _ in range(3):
             step()
