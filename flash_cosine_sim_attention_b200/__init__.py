@@ -9,5 +9,6 @@ from .flash_cosine_sim_attention import (  # noqa: F401
     flash_cosine_sim_attention_cuda,
     l2norm_tensors,
     plain_cosine_sim_attention,
+    release_workspaces,
 )
 from .version import __version__  # noqa: F401

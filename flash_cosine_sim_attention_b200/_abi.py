@@ -38,6 +38,8 @@ EXPORTED_SYMBOLS = (
     "fcsa_backward_fused",
     "fcsa_forward_bias",
     "fcsa_backward_bias",
+    "fcsa_f32_cast",
+    "fcsa_f32_cast_backward",
 )
 
 
@@ -128,6 +130,10 @@ def load():
     lib.fcsa_backward_bias.restype = c_int32
     lib.fcsa_backward_bias.argtypes = [PP, PT, PT, PT, PT, PT, c_void_p, PB, c_void_p, c_int64, c_int64,
                                        PT, PT, PT, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
+    lib.fcsa_f32_cast.restype = c_int32
+    lib.fcsa_f32_cast.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.fcsa_f32_cast_backward.restype = c_int32
+    lib.fcsa_f32_cast_backward.argtypes = [c_int32] * 6 + [PT, PT, c_void_p, PT, c_void_p, c_int32, c_void_p]
     lib.fcsa_set_kernel_events.restype = c_int32
     lib.fcsa_set_kernel_events.argtypes = [c_int32, c_void_p, c_void_p]
     _lib = lib

@@ -407,6 +407,68 @@ int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_
                        zeroed, zeroed_bytes, stream, n->q_rnorm, n->k_rnorm, n->groups);
 }
 
+static int f32_cast_common(fcsa::F32CastArgs& a, int32_t dtype, int32_t B, int32_t H, int32_t N, int32_t D, int32_t G,
+                           const fcsa_tensor* x, const fcsa_tensor* y) {
+  if (dtype != FCSA_F16 && dtype != FCSA_BF16) return fail(FCSA_ERR_UNSUPPORTED, "f32 cast: 16-bit dtype %d not implemented", dtype);
+  if (B <= 0 || H <= 0 || N <= 0) return fail(FCSA_ERR_INVALID, "f32 cast: empty tensor");
+  if (D != 16 && D != 32 && D != 64 && D != 128) return fail(FCSA_ERR_UNSUPPORTED, "f32 cast: head_dim %d not implemented", D);
+  if (G < 0 || (G > 0 && (D % G != 0 || ((D / G) & (D / G - 1)) != 0)))
+    return fail(FCSA_ERR_INVALID, "f32 cast: groups %d must divide %d into power-of-two chunks", G, D);
+  if (!x || !x->ptr || !y) return fail(FCSA_ERR_INVALID, "f32 cast: null tensor");
+  if ((reinterpret_cast<uintptr_t>(x->ptr) & 15u) || (x->sb % 4) || (x->sh % 4) || (x->sn % 4))
+    return fail(FCSA_ERR_INVALID, "f32 cast: float32 rows must be 16-byte aligned");
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.N = N; a.D = D; a.G = G;
+  a.x = reinterpret_cast<const float*>(x->ptr); a.x_sb = x->sb; a.x_sh = x->sh; a.x_sn = x->sn;
+  a.y = y->ptr; a.y_sb = y->sb; a.y_sh = y->sh; a.y_sn = y->sn;
+  return FCSA_OK;
+}
+
+int fcsa_f32_cast(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim, int32_t groups,
+                  const fcsa_tensor* x, const fcsa_tensor* y, float* rnorm, const float* mul, int32_t mul_reciprocal,
+                  void* stream) {
+  fcsa::F32CastArgs a;
+  int r;
+  if ((r = f32_cast_common(a, dtype, batch, heads, rows, head_dim, groups, x, y))) return r;
+  if ((r = check_tensor(y, "y"))) return r;
+  if (groups > 0 && !rnorm) return fail(FCSA_ERR_INVALID, "f32 cast: rnorm is null");
+  a.rnorm = rnorm; a.mul = mul; a.mul_reciprocal = mul_reciprocal;
+  const int rpb = 256 / (head_dim / 8);
+  const long long total = (long long)batch * heads * rows;
+  const unsigned grid = (unsigned)((total + rpb - 1) / rpb);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == FCSA_BF16) fcsa::f32_cast_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a);
+  else fcsa::f32_cast_kernel<__half><<<grid, 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "f32 cast launch");
+  g_launches.fetch_add(1);
+  return FCSA_OK;
+}
+
+int fcsa_f32_cast_backward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,
+                           int32_t groups, const fcsa_tensor* dy, const fcsa_tensor* y, const float* rnorm,
+                           const fcsa_tensor* dx, const float* mul, int32_t mul_reciprocal, void* stream) {
+  fcsa::F32CastArgs a;
+  int r;
+  fcsa_tensor ynull = {nullptr, 0, 0, 0};
+  if ((r = f32_cast_common(a, dtype, batch, heads, rows, head_dim, groups, dy, groups > 0 ? y : &ynull))) return r;
+  if (groups > 0 && ((r = check_tensor(y, "y")) || !rnorm)) return r ? r : fail(FCSA_ERR_INVALID, "f32 cast backward: rnorm is null");
+  if (!dx || !dx->ptr || (reinterpret_cast<uintptr_t>(dx->ptr) & 15u) || (dx->sb % 4) || (dx->sh % 4) || (dx->sn % 4))
+    return fail(FCSA_ERR_INVALID, "f32 cast backward: dx rows must be 16-byte aligned float32");
+  a.dx = reinterpret_cast<float*>(dx->ptr); a.o_sb = dx->sb; a.o_sh = dx->sh; a.o_sn = dx->sn;
+  a.rnorm = const_cast<float*>(rnorm); a.mul = mul; a.mul_reciprocal = mul_reciprocal;
+  const int rpb = 256 / (head_dim / 8);
+  const long long total = (long long)batch * heads * rows;
+  const unsigned grid = (unsigned)((total + rpb - 1) / rpb);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == FCSA_BF16) fcsa::f32_cast_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a);
+  else fcsa::f32_cast_bwd_kernel<__half><<<grid, 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "f32 cast backward launch");
+  g_launches.fetch_add(1);
+  return FCSA_OK;
+}
+
 int fcsa_l2norm_forward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,
                         int32_t groups, const fcsa_tensor* x, const fcsa_tensor* y, float* rnorm,
                         void* stream) {

@@ -209,6 +209,158 @@ __global__ void __launch_bounds__(256) l2norm_fwd_pair_kernel(const L2PairArgs p
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// float32 front end (reference: Float is dispatched in forward and backward, cu:1702-1703 / 1832-1834).  float32
+// callers run on the 16-bit tensor-core kernels; these two passes are the only extra work around them:
+//   f32_cast_kernel     : y(16 bit) = round( x / max(||x||_group, 1e-12) * mul )   G > 0: l2norm over G groups
+//                                     round( x * mul )                              G = 0: plain scaled cast
+//                         `mul` is an optional DEVICE scalar (the power-of-two range scale of v / dO, chosen on
+//                         the device - no host synchronisation); rnorm (fp32, per group) is kept for the backward
+//   f32_cast_bwd_kernel : dx(f32) = (dy - y <y, dy>_group) * rnorm_group * mul      G > 0   (dy: f32 gradient
+//                                   dy * mul                                         G = 0    w.r.t. y; y: 16 bit)
+// One thread owns 8 features (two float4 loads); TPR threads per row.
+// ------------------------------------------------------------------------------------------------
+struct F32CastArgs {
+  int B, H, N, D, G;
+  long long x_sb, x_sh, x_sn;     // float32 tensor (x forward, dy / dx backward): element strides
+  long long y_sb, y_sh, y_sn;     // 16-bit tensor y
+  long long o_sb, o_sh, o_sn;     // backward only: dx (float32)
+  const float* x;
+  void* y;
+  float* dx;
+  float* rnorm;                   // (B, H, N, G) fp32 or nullptr (G = 0)
+  const float* mul;               // device scalar or nullptr (= 1)
+  int mul_reciprocal;             // 1: use 1 / *mul
+};
+
+__device__ __forceinline__ float f32cast_mul(const F32CastArgs& a) {
+  if (a.mul == nullptr) return 1.f;
+  const float m = __ldg(a.mul);
+  return a.mul_reciprocal ? 1.f / m : m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) f32_cast_kernel(const F32CastArgs a) {
+  const int tpr = a.D >> 3;
+  const int rpb = 256 / tpr;
+  const long long row = (long long)blockIdx.x * rpb + threadIdx.x / tpr;
+  const int tr = threadIdx.x % tpr;
+  const long long total = (long long)a.B * a.H * a.N;
+  const bool ok = row < total;
+  const long long rr = ok ? row : 0;
+  const int n = (int)(rr % a.N);
+  const int h = (int)((rr / a.N) % a.H);
+  const int b = (int)(rr / ((long long)a.N * a.H));
+  const float* xp = a.x + b * a.x_sb + h * a.x_sh + (long long)n * a.x_sn + tr * 8;
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+  if (ok) {
+    lo = __ldg(reinterpret_cast<const float4*>(xp));
+    hi = __ldg(reinterpret_cast<const float4*>(xp + 4));
+  }
+  float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  const float mul = f32cast_mul(a);
+  float rn[8];
+  if (a.G == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rn[i] = mul;
+  } else {
+    const int gs = a.D / a.G;
+    if (gs >= 8) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+      const int tpg = gs >> 3;
+      ss = group_reduce(ss, tpg);
+      const float r = rnorm_of(ss);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rn[i] = r * mul;
+      if (ok && a.rnorm && (tr & (tpg - 1)) == 0) a.rnorm[row * a.G + tr / tpg] = r;
+    } else {
+      float sq[8], ss[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sq[i] = f[i] * f[i];
+      subgroup_sums8(sq, gs, ss);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float r = rnorm_of(ss[i]);
+        rn[i] = r * mul;
+        if (ok && a.rnorm && (i & (gs - 1)) == 0) a.rnorm[row * a.G + (tr * 8 + i) / gs] = r;
+      }
+    }
+  }
+  if (ok) {
+    uint4 w;
+    w.x = pack2<T>(f[0] * rn[0], f[1] * rn[1]);
+    w.y = pack2<T>(f[2] * rn[2], f[3] * rn[3]);
+    w.z = pack2<T>(f[4] * rn[4], f[5] * rn[5]);
+    w.w = pack2<T>(f[6] * rn[6], f[7] * rn[7]);
+    T* yp = reinterpret_cast<T*>(a.y) + b * a.y_sb + h * a.y_sh + (long long)n * a.y_sn + tr * 8;
+    *reinterpret_cast<uint4*>(yp) = w;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) f32_cast_bwd_kernel(const F32CastArgs a) {
+  const int tpr = a.D >> 3;
+  const int rpb = 256 / tpr;
+  const long long row = (long long)blockIdx.x * rpb + threadIdx.x / tpr;
+  const int tr = threadIdx.x % tpr;
+  const long long total = (long long)a.B * a.H * a.N;
+  const bool ok = row < total;
+  const long long rr = ok ? row : 0;
+  const int n = (int)(rr % a.N);
+  const int h = (int)((rr / a.N) % a.H);
+  const int b = (int)(rr / ((long long)a.N * a.H));
+  const float* dyp = a.x + b * a.x_sb + h * a.x_sh + (long long)n * a.x_sn + tr * 8;
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+  uint4 ry = make_uint4(0, 0, 0, 0);
+  if (ok) {
+    lo = __ldg(reinterpret_cast<const float4*>(dyp));
+    hi = __ldg(reinterpret_cast<const float4*>(dyp + 4));
+    if (a.G > 0)
+      ry = ldg_stream128(reinterpret_cast<const T*>(a.y) + b * a.y_sb + h * a.y_sh + (long long)n * a.y_sn + tr * 8);
+  }
+  float dy[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  const float mul = f32cast_mul(a);
+  float out[8];
+  if (a.G == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = dy[i] * mul;
+  } else {
+    float y[8];
+    {
+      const float2 u0 = unpack2<T>(ry.x), u1 = unpack2<T>(ry.y), u2 = unpack2<T>(ry.z), u3 = unpack2<T>(ry.w);
+      y[0] = u0.x; y[1] = u0.y; y[2] = u1.x; y[3] = u1.y; y[4] = u2.x; y[5] = u2.y; y[6] = u3.x; y[7] = u3.y;
+    }
+    const int gs = a.D / a.G;
+    if (gs >= 8) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot += y[i] * dy[i];
+      const int tpg = gs >> 3;
+      dot = group_reduce(dot, tpg);
+      const float r = (ok ? a.rnorm[row * a.G + tr / tpg] : 0.f) * mul;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] = (dy[i] - y[i] * dot) * r;
+    } else {
+      float pr[8], dot[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pr[i] = y[i] * dy[i];
+      subgroup_sums8(pr, gs, dot);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float r = (ok ? a.rnorm[row * a.G + (tr * 8 + i) / gs] : 0.f) * mul;
+        out[i] = (dy[i] - y[i] * dot[i]) * r;
+      }
+    }
+  }
+  if (ok) {
+    float* op = a.dx + b * a.o_sb + h * a.o_sh + (long long)n * a.o_sn + tr * 8;
+    *reinterpret_cast<float4*>(op) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(out[4], out[5], out[6], out[7]);
+  }
+}
+
 // dx = (dy - y * <y, dy>_group) * rnorm_group
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const L2Args a) {

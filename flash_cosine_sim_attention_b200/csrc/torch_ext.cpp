@@ -200,6 +200,57 @@ Tensor l2norm_backward(const Tensor& dy_in, const Tensor& y_in, const Tensor& rn
 }
 
 // ------------------------------------------------------------------------------------------------
+// float32 front end: (l2norm +) cast of a float32 tensor to the 16-bit operand dtype, and its backward
+// ------------------------------------------------------------------------------------------------
+// x: float32 (b, h, n, d) or (b, n, d); returns y (16 bit, `pad_to` >= d features, zero-padded) and rnorm (groups > 0)
+std::tuple<Tensor, Tensor> f32_cast(const Tensor& x_in, bool to_bf16, int64_t groups, const optional<Tensor>& mul,
+                                    bool mul_reciprocal, int64_t pad_to) {
+  TORCH_CHECK(x_in.is_cuda() && x_in.scalar_type() == at::kFloat && (x_in.dim() == 3 || x_in.dim() == 4),
+              "f32_cast: 3-D or 4-D float32 CUDA tensor expected");
+  const c10::cuda::CUDAGuard guard(x_in.device());
+  const Tensor x = (x_in.stride(-1) == 1 && reinterpret_cast<uintptr_t>(x_in.data_ptr()) % 16 == 0) ? x_in : x_in.contiguous();
+  const int64_t B = x.size(0), H = x.dim() == 4 ? x.size(1) : 1, N = x.size(-2), D = x.size(-1);
+  std::vector<int64_t> shape = x.sizes().vec();
+  shape.back() = std::max(pad_to, D);
+  const auto hopt = x.options().dtype(to_bf16 ? at::kBFloat16 : at::kHalf);
+  Tensor y = shape.back() == D ? at::empty(shape, hopt) : at::zeros(shape, hopt);
+  Tensor rnorm;
+  if (groups > 0) rnorm = at::empty({B, H, N, groups}, x.options());
+  const fcsa_tensor tx = view4(x), ty = view4(y);
+  FCSA_CHECK(fcsa_f32_cast(to_bf16 ? FCSA_BF16 : FCSA_F16, (int32_t)B, (int32_t)H, (int32_t)N, (int32_t)D, (int32_t)groups,
+                           &tx, &ty, groups > 0 ? rnorm.data_ptr<float>() : nullptr,
+                           (mul.has_value() && mul->defined()) ? mul->data_ptr<float>() : nullptr, mul_reciprocal ? 1 : 0,
+                           at::cuda::getCurrentCUDAStream().stream()));
+  return {y, rnorm};
+}
+
+// dy: float32 gradient w.r.t. y (may carry padded features: only the first d are read); y / rnorm: what f32_cast
+// returned (groups > 0); returns the float32 gradient w.r.t. x with d features
+Tensor f32_cast_backward(const Tensor& dy_in, const optional<Tensor>& y, const optional<Tensor>& rnorm, int64_t groups,
+                         const optional<Tensor>& mul, bool mul_reciprocal, int64_t d) {
+  TORCH_CHECK(dy_in.is_cuda() && dy_in.scalar_type() == at::kFloat, "f32_cast_backward: float32 CUDA gradient expected");
+  const c10::cuda::CUDAGuard guard(dy_in.device());
+  const Tensor dy = (dy_in.stride(-1) == 1 && reinterpret_cast<uintptr_t>(dy_in.data_ptr()) % 16 == 0) ? dy_in : dy_in.contiguous();
+  const int64_t B = dy.size(0), H = dy.dim() == 4 ? dy.size(1) : 1, N = dy.size(-2);
+  std::vector<int64_t> shape = dy.sizes().vec();
+  shape.back() = d;
+  Tensor dx = at::empty(shape, dy.options());
+  const fcsa_tensor tdy = view4(dy), tdx = view4(dx);
+  fcsa_tensor ty = {nullptr, 0, 0, 0};
+  bool bf = false;
+  if (groups > 0) {
+    TORCH_CHECK(y.has_value() && y->defined() && rnorm.has_value() && rnorm->defined(), "f32_cast_backward: y and rnorm needed");
+    ty = view4(*y);
+    bf = y->scalar_type() == at::kBFloat16;
+  }
+  FCSA_CHECK(fcsa_f32_cast_backward(bf ? FCSA_BF16 : FCSA_F16, (int32_t)B, (int32_t)H, (int32_t)N, (int32_t)d,
+                                    (int32_t)groups, &tdy, &ty, groups > 0 ? rnorm->data_ptr<float>() : nullptr, &tdx,
+                                    (mul.has_value() && mul->defined()) ? mul->data_ptr<float>() : nullptr,
+                                    mul_reciprocal ? 1 : 0, at::cuda::getCurrentCUDAStream().stream()));
+  return dx;
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward_ex: the general forward.
 //   l2norm_groups > 0 : q, k are RAW; they are normalised over that many groups by the fused pre-pass
 //                       (returns q_hat, k_hat, q_rnorm, k_rnorm for the backward); no bias on this path
@@ -347,6 +398,20 @@ std::tuple<Tensor, Tensor, Tensor, optional<Tensor>> backward(
   return {std::get<0>(r), std::get<1>(r), std::get<2>(r), db};
 }
 
+// Drops the cached backward workspaces of every (device, stream) (they only ever grow: a long-context call leaves a
+// 1 GB accumulator behind).  Returns the number of bytes released to the caching allocator.  Safe at any time between
+// calls: buffers still referenced by enqueued kernels stay alive through the allocator's stream semantics.
+int64_t release_workspaces() {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  int64_t bytes = 0;
+  for (auto& kv : g_ws) {
+    if (kv.second.scratch.defined()) bytes += kv.second.scratch.numel();
+    if (kv.second.zeroed.defined()) bytes += kv.second.zeroed.numel();
+  }
+  g_ws.clear();
+  return bytes;
+}
+
 // the reference's debug() is an empty hook (cu:1921); this one reports the library's launch counter
 int64_t debug() { return fcsa_debug(); }
 
@@ -365,8 +430,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("forward_ex", &forward_ex, "forward with explicit shift / fused l2norm / prepared bias");
   m.def("backward_ex", &backward_ex, "backward of forward_ex");
   m.def("prepare_bias", &prepare_bias, "attn_bias -> padded, aligned tensor in the problem dtype");
+  m.def("f32_cast", &f32_cast, "float32 -> (l2norm +) scaled cast to the 16-bit operand dtype");
+  m.def("f32_cast_backward", &f32_cast_backward, "backward of f32_cast: float32 gradient w.r.t. the float32 input");
   m.def("l2norm_forward", &l2norm_forward, "grouped l2norm: x -> (y, 1/norm)");
   m.def("l2norm_backward", &l2norm_backward, "grouped l2norm backward from the normalised y");
+  m.def("release_workspaces", &release_workspaces, "free the cached backward workspaces; returns the bytes released");
   m.def("abi_version", []() { return fcsa_version(); });
   m.def("_error_path_selftest", []() { FCSA_CHECK(fcsa_forward(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); },
         "raises the library's error for a null problem (exercises the C ABI error -> Python exception path)");

@@ -35,6 +35,7 @@ __all__ = [
     "forward",
     "backward",
     "debug",
+    "release_workspaces",
 ]
 
 _KERNEL_DTYPES = {torch.float16: _abi.FCSA_F16, torch.bfloat16: _abi.FCSA_BF16}
@@ -179,6 +180,12 @@ def backward(d_out, o, inv_l, q, k, v, mask, attn_bias, attn_bias_batch_dim, sca
 def debug():
     """Reference: a no-op hook (cu:1921).  Here: number of kernels launched by the library."""
     return int(_ext().debug())
+
+
+def release_workspaces():
+    """Free the backward workspaces cached per (device, stream) - the fp32 dq accumulator and the scratch area
+    only ever grow with the largest problem seen.  Returns the number of bytes handed back to the allocator."""
+    return int(_ext().release_workspaces())
 
 
 class FlashCosineSimAttention(Function):
@@ -358,27 +365,52 @@ def plain_cosine_sim_attention(q, k, v, mask=None, attn_bias=None, scale=8, grou
 # Every op around the kernels is an asynchronous elementwise torch op: no host synchronisation.
 # --------------------------------------------------------------------------------------------
 def _pow2_scale(t, top_exp):
-    """Power of two s (0-dim fp32 tensor, on t's device) with amax|t| / s in [2^(top_exp-1), 2^top_exp)."""
-    amax = t.detach().abs().amax().float().clamp_min(1e-30)
+    """Power of two s (1-element fp32 tensor, on t's device) with amax|t| / s in [2^(top_exp-1), 2^top_exp)."""
+    amax = torch.linalg.vector_norm(t.detach(), float("inf")).float().clamp_min(1e-30).reshape(1)
     return torch.exp2(torch.floor(torch.log2(amax)) + 1 - top_exp)
 
 
+_F32_CAST_DIMS = (16, 32, 64, 128)
+
+
+def _cast16(x, half, groups, mul, reciprocal, Dp):
+    """float32 x -> ((l2norm over `groups` +) scaled) 16-bit tensor with Dp >= D zero-padded features, and rnorm.
+    One fused CUDA pass (fcsa_f32_cast) for head dims 16 / 32 / 64 / 128; other multiples of 8 (96) take torch ops."""
+    D = x.shape[-1]
+    if D in _F32_CAST_DIMS and x.ndim in (3, 4):
+        return _ext().f32_cast(x, half == torch.bfloat16, groups, mul, reciprocal, Dp)
+    assert groups == 0
+    y = x if mul is None else (x / mul if reciprocal else x * mul)
+    y = y.to(half)
+    return (torch.nn.functional.pad(y, (0, Dp - D)) if Dp > D else y), None
+
+
+def _uncast16(dy, y, rnorm, groups, mul, reciprocal, D):
+    """Backward of _cast16: float32 gradient w.r.t. y (possibly padded) -> float32 gradient w.r.t. x."""
+    if D in _F32_CAST_DIMS and dy.ndim in (3, 4):
+        return _ext().f32_cast_backward(dy, y, rnorm, groups, mul, reciprocal, D)
+    assert groups == 0
+    g = dy[..., :D]
+    return g if mul is None else (g / mul if reciprocal else g * mul)
+
+
 class _Float32OnHalfKernels(Function):
-    """float32 q_hat, k_hat (already normalised if wanted), v (+ bias) -> float32 o, on the 16-bit kernels:
-    operands are rounded to `half` (fp16: 11-bit significand, tf32's; bf16 when fp16's exponent range is too
-    small), v and the incoming gradient are brought to [1, 2) by an exact power-of-two scale chosen on the
-    device (the kernels form dP = dO V^T and dS = P (dP - delta) in the 16-bit range, so operands keep headroom),
-    accumulation is fp32 and the results are written as float32 straight from the accumulators (out_f32)."""
+    """float32 q, k, v (+ bias) -> float32 o, on the 16-bit kernels: operands are rounded to `half` (fp16: 11-bit
+    significand, tf32's; bf16 when fp16's exponent range is too small), v and the incoming gradient are brought to
+    [1, 2) by an exact power-of-two scale chosen on the device (the kernels form dP = dO V^T and dS = P (dP - delta) in
+    the 16-bit range, so operands keep headroom), accumulation is fp32 and the results are written as float32 straight
+    from the accumulators (out_f32).  norm_groups > 0: q, k arrive RAW and are l2-normalised by the cast pass itself
+    (its backward is the cast pass of the gradients); 0: they are used as given."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim, shift, half, use_amax):
+    def forward(ctx, q, k, v, mask, attn_bias, scale, causal, attn_bias_batch_dim, shift, half, use_amax, norm_groups):
         ext = _ext()
         D = q.shape[-1]
+        Dp = D if D in _KERNEL_HEAD_DIMS else (64 if D < 64 else 128)        # 16 / 32 / 96: zero-padded features
         sv = _pow2_scale(v, 1)
-        qh, kh, vh = q.to(half), k.to(half), (v / sv).to(half)
-        if D not in _KERNEL_HEAD_DIMS:          # head dims 16 / 32 / 96 (reference cu:84): zero-padded features
-            Dp = 64 if D < 64 else 128
-            qh, kh, vh = (torch.nn.functional.pad(t, (0, Dp - D)) for t in (qh, kh, vh))
+        qh, rq = _cast16(q, half, norm_groups, None, False, Dp)
+        kh, rk = _cast16(k, half, norm_groups, None, False, Dp)
+        vh, _ = _cast16(v, half, 0, sv, True, Dp)
         batch_dim = bool(attn_bias_batch_dim) or q.ndim == 3
         bias = amax = None
         if exists(attn_bias):
@@ -388,23 +420,25 @@ class _Float32OnHalfKernels(Function):
         needs_grad = any(ctx.needs_input_grad[:3]) or (exists(attn_bias) and ctx.needs_input_grad[4])
         o, inv_l = ext.forward_ex(qh, kh, vh, mask, bias, batch_dim, amax, scale, shift, causal, 0, needs_grad, True)[:2]
         if needs_grad:
-            ctx.save_for_backward(o, inv_l, qh, kh, vh, mask, bias, amax, sv)
-            ctx.params = (scale, shift, causal, batch_dim, D, exists(attn_bias) and ctx.needs_input_grad[4])
+            ctx.save_for_backward(o, inv_l, qh, kh, vh, mask, bias, amax, sv, rq, rk)
+            ctx.params = (scale, shift, causal, batch_dim, D, exists(attn_bias) and ctx.needs_input_grad[4], norm_groups)
         return o[..., :D] * sv
 
     @staticmethod
     def backward(ctx, g):
-        o, inv_l, qh, kh, vh, mask, bias, amax, sv = ctx.saved_tensors
-        scale, shift, causal, batch_dim, D, bias_grad = ctx.params
-        g = g * sv                                            # d(o_kernel) ; o = o_kernel * sv
-        sg = _pow2_scale(g, 1)
-        gh = (g / sg).to(qh.dtype)
-        if gh.shape[-1] != qh.shape[-1]:
-            gh = torch.nn.functional.pad(gh, (0, qh.shape[-1] - gh.shape[-1]))
+        o, inv_l, qh, kh, vh, mask, bias, amax, sv, rq, rk = ctx.saved_tensors
+        scale, shift, causal, batch_dim, D, bias_grad, norm_groups = ctx.params
+        # o = o_kernel * sv, so d(o_kernel) = g * sv; it enters the kernels as fp16 scaled into [1, 2):
+        # g * sv / sg with sg = pg * sv, pg = pow2 scale of g  ->  the cast pass computes g / pg
+        pg = _pow2_scale(g, 1)
+        gh, _ = _cast16(g, qh.dtype, 0, pg, True, qh.shape[-1])
         dq, dk, dv, db = _ext().backward_ex(gh, o, inv_l, qh, kh, vh, None, None, mask, bias, batch_dim, amax,
                                             bias_grad, None, scale, shift, causal, 0, True)
-        dq, dk, dv = dq[..., :D] * sg, dk[..., :D] * sg, dv[..., :D] * (sg / sv)
-        return dq, dk, dv, None, (db * sg if bias_grad else None), None, None, None, None, None, None
+        sg = pg * sv                                          # undo the gradient scale; dv also undoes v / sv
+        dq = _uncast16(dq, qh, rq, norm_groups, sg, False, D)
+        dk = _uncast16(dk, kh, rk, norm_groups, sg, False, D)
+        dv = _uncast16(dv, None, None, 0, pg, False, D)
+        return dq, dk, dv, None, (db * sg if bias_grad else None), None, None, None, None, None, None, None
 
 
 def _float32_on_half_kernels(q, k, v, mask, attn_bias, scale, groups, causal, l2norm_qk, attn_bias_batch_dim):
@@ -417,11 +451,16 @@ def _float32_on_half_kernels(q, k, v, mask, attn_bias, scale, groups, causal, l2
         _warn_once("f32-bf16", "flash_cosine_sim_attention: float32 inputs with scale*groups > "
                                f"{_FP16_GROUPED_RANGE:g} (or l2norm_qk=False) run on the bfloat16 kernels - fp16's "
                                "exponent range cannot hold exp(scale*q.k) there; operands carry 8 significant bits")
+    gs = D // groups
+    norm_groups = 0
     if l2norm_qk:
-        q, k = _l2norm_torch(q, groups), _l2norm_torch(k, groups)           # fp32, differentiable
+        if D in _F32_CAST_DIMS and (gs & (gs - 1)) == 0 and q.ndim in (3, 4):
+            norm_groups = groups                                              # fused into the cast pass
+        else:
+            q, k = _l2norm_torch(q, groups), _l2norm_torch(k, groups)       # fp32, differentiable
     shift = _choose_shift(h, scale, groups if l2norm_qk else 1, l2norm_qk)
     return _Float32OnHalfKernels.apply(q, k, v, mask, attn_bias, float(scale), bool(causal), bool(attn_bias_batch_dim),
-                                       float(shift), h, bool(l2norm_qk and h == torch.float16))
+                                       float(shift), h, bool(l2norm_qk and h == torch.float16), int(norm_groups))
 
 
 _warned = set()

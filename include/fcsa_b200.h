@@ -174,6 +174,24 @@ int fcsa_backward_fused(const fcsa_problem* p, const fcsa_l2norm* n, const fcsa_
                         void* workspace, size_t workspace_bytes, void* zeroed, size_t zeroed_bytes,
                         void* stream);
 
+/* ---- float32 front end ---------------------------------------------------------------------------
+ * The reference dispatches Float in forward and backward (cu:1702-1703, 1832-1834).  Here float32 callers run the
+ * 16-bit tensor-core kernels (fp32 accumulation, `out_f32` results); these two passes are all that surrounds them.
+ * `x` / `dy` / `dx` are FLOAT32 tensors (fcsa_tensor with float32 element strides, feature dim contiguous, rows
+ * 16-byte aligned), `y` is the 16-bit tensor (`dtype`), which may be wider than head_dim (zero-padded features are
+ * the caller's business: only head_dim features per row are written / read).
+ *   fcsa_f32_cast          y = round16( l2norm_groups(x) * m )   groups > 0 ;  round16( x * m )   groups == 0
+ *   fcsa_f32_cast_backward dx = (dy - y <y,dy>_group) * rnorm_group * m   groups > 0 ;  dy * m   groups == 0
+ * m = 1 if `mul` is NULL, else *mul (a DEVICE scalar - e.g. a power-of-two range scale chosen on the device, the
+ * host never reads it), or 1 / *mul when mul_reciprocal != 0.  rnorm: (batch, heads, rows, groups) fp32.
+ * head_dim must be 16, 32, 64 or 128 and head_dim / groups a power of two. */
+int fcsa_f32_cast(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim, int32_t groups,
+                  const fcsa_tensor* x, const fcsa_tensor* y, float* rnorm, const float* mul, int32_t mul_reciprocal,
+                  void* stream);
+int fcsa_f32_cast_backward(int32_t dtype, int32_t batch, int32_t heads, int32_t rows, int32_t head_dim,
+                           int32_t groups, const fcsa_tensor* dy, const fcsa_tensor* y, const float* rnorm,
+                           const fcsa_tensor* dx, const float* mul, int32_t mul_reciprocal, void* stream);
+
 /* ---- additive attention bias -------------------------------------------------------------------
  * Replaces the `attn_bias` / `attn_bias_batch_dim` arguments of the reference's forward / backward
  * (flash_cosine_sim_attention_cuda.cu:1630-1639, 1752-1764; added to the logits at cu:1168,1214 and

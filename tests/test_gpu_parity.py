@@ -347,6 +347,13 @@ def test_zeroed_workspace_is_left_clean_across_shapes(fcsa):
     check(fcsa, (1, 2, 456, 64), (1, 2, 200, 64), torch.bfloat16, seed=7, causal=True)
 
 
+def test_release_workspaces(fcsa):
+    check(fcsa, (1, 2, 256, 64), (1, 2, 256, 64), torch.bfloat16, seed=71, causal=True)
+    assert fcsa.release_workspaces() > 0
+    assert fcsa.release_workspaces() == 0
+    check(fcsa, (1, 2, 256, 64), (1, 2, 256, 64), torch.bfloat16, seed=72, causal=True)      # re-created on demand
+
+
 def test_many_batch_heads_merged(fcsa):
     """batch*heads > 65535 (merged 3-D layout) must run forward AND backward."""
     dt = torch.float16
