@@ -10,8 +10,10 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "../../include/fcsa_b200.h"
@@ -140,8 +142,12 @@ int launch_forward(const fcsa_problem* p, const fcsa_tensor* q, const fcsa_tenso
     cudaError_t e = fcsa::ensure_dynamic_smem<fcsa::fcsa_fwd_kernel<T, D, BIAS>>(Cfg::kSmem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fwd)");
   }
-  const long long grid = (long long)a.n_qblk * p->batch * p->heads;
-  if (grid > 0x7FFFFFFFLL) return fail(FCSA_ERR_INVALID, "problem too large for one launch");
+  // persistent CTAs: one per SM, each walking its share of the (query block, batch, head) work items
+  const long long items = (long long)a.n_qblk * p->batch * p->heads;
+  if (items > 0x7FFFFFFFLL) return fail(FCSA_ERR_INVALID, "problem too large for one launch");
+  // FCSA_FWD_GRID (tuning / A-B knob): number of CTAs; 0 = one CTA per work item (not persistent)
+  static const long long grid_env = [] { const char* e = getenv("FCSA_FWD_GRID"); return e ? atoll(e) : -1LL; }();
+  const long long grid = grid_env == 0 ? items : std::min<long long>(items, grid_env > 0 ? grid_env : sm_count());
   if (g_ev[0][0]) cudaEventRecord(g_ev[0][0], stream);
   cudaError_t e = fcsa::launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, a);
   if (g_ev[0][1]) cudaEventRecord(g_ev[0][1], stream);

@@ -65,7 +65,7 @@ struct FwdCfg {
   static constexpr int kOffK = 2 * kTile;
   static constexpr int kOffV = kOffK + kKS * kTile;
   static constexpr int kOffL = kOffV + kVS * kTile;   // partial row sums: 2 tiles x 2 halves x 128 floats
-  static constexpr int kOffBar = kOffL + 2048;
+  static constexpr int kOffBar = kOffL + 4096;        // (double-buffered over work items)
   static constexpr int kSmem = kOffBar + 256 + 1024;  // + alignment slack
   static constexpr int kThreads = 640;                // 16 softmax warps + 4 service warps
 };
@@ -88,9 +88,11 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // barrier indices
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS,
+  constexpr int Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS,
                 V_EMPTY = V_FULL + VS, S_FULL = V_EMPTY + VS, P_FULL = S_FULL + 2,
-                O_FULL = P_FULL + 2, S_FREE = O_FULL + 2, P_FREE = S_FREE + 2, NBARS = P_FREE + 2;
+                O_FULL = P_FULL + 2, S_FREE = O_FULL + 2, P_FREE = S_FREE + 2, O_FREE = P_FREE + 2,
+                NBARS = O_FREE + 2;
+  static_assert(NBARS * 8 + 4 <= 256, "barrier area");
   constexpr bool PSEP = (D == 64);     // P in its own TMEM columns (see header comment)
   constexpr int kPolyEvery = (D == 64) ? FCSA_POLY_EVERY : 8;   // 1 of every N exp pairs is emulated on the FMA pipe
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
@@ -98,38 +100,57 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
 
-  // ---- which work item ---------------------------------------------------------------
+  // ---- work items -------------------------------------------------------------------
+  // One item = 256 query rows of one (batch, head).  Items are numbered heaviest first (causal: the
+  // lowest query blocks see the fewest keys) and dealt to the CTAs of the grid in snake order
+  // (round r: item r*G + c, or r*G + G-1-c on odd rounds), which balances as well as the hardware's
+  // own longest-first dispatch of one CTA per item.  With a grid of one CTA per SM the CTA is
+  // persistent: barriers, TMEM and the K/V ring live on across items, the next item's Q / K / V are
+  // prefetched under the current item's last tiles and one tile's epilogue runs under the other tile's
+  // MMAs.  (A grid of n_items CTAs degenerates to one item per CTA.)
   const int bh_count = a.B * a.H;
-  const int rank = blockIdx.x / bh_count;
-  const int bh = blockIdx.x - rank * bh_count;
-  const int qblk = a.causal ? (a.n_qblk - 1 - rank) : rank;   // heaviest causal blocks first
-  const int b = bh / a.H, h = bh - b * a.H;
-  const int hk = (a.kv_heads == 1) ? 0 : h;
-  const int m0 = qblk * 256;
+  const int n_items = a.n_qblk * bh_count;
   const int off = a.Nk - a.Nq;
   const int nkt = (a.Nk + 127) >> 7;
-  int n_t[2];
+  struct Item {
+    int b, h, hk, m0, n_t[2], NT;
+  };
+  auto item_index = [&](int r) -> int {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int idx = r * G + ((r & 1) ? (G - 1 - c) : c);
+    return idx < n_items ? idx : -1;
+  };
+  auto load_item = [&](int idx) -> Item {
+    Item it;
+    const int rank = idx / bh_count;
+    const int bh = idx - rank * bh_count;
+    const int qblk = a.causal ? (a.n_qblk - 1 - rank) : rank;   // heaviest causal blocks first
+    it.b = bh / a.H;
+    it.h = bh - it.b * a.H;
+    it.hk = (a.kv_heads == 1) ? 0 : it.h;
+    it.m0 = qblk * 256;
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int row_lo = m0 + 128 * t;
-    if (row_lo >= a.Nq) {
-      n_t[t] = 0;
-    } else if (!a.causal) {
-      n_t[t] = nkt;
-    } else {
-      const int row_hi = min(row_lo + 127, a.Nq - 1);
-      const int last_col = row_hi + off;
-      n_t[t] = last_col < 0 ? 0 : min(nkt, (last_col >> 7) + 1);
+    for (int t = 0; t < 2; ++t) {
+      const int row_lo = it.m0 + 128 * t;
+      if (row_lo >= a.Nq) {
+        it.n_t[t] = 0;
+      } else if (!a.causal) {
+        it.n_t[t] = nkt;
+      } else {
+        const int row_hi = min(row_lo + 127, a.Nq - 1);
+        const int last_col = row_hi + off;
+        it.n_t[t] = last_col < 0 ? 0 : min(nkt, (last_col >> 7) + 1);
+      }
     }
-  }
-  const int NT = max(n_t[0], n_t[1]);
+    it.NT = max(it.n_t[0], it.n_t[1]);
+    return it;
+  };
 
   // ---- one-time setup ------------------------------------------------------------------
   if (warp == 16 && elect_one()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    mbar_init(BAR(Q_FULL), 1);
     for (int i = 0; i < KS; ++i) {
       mbar_init(BAR(K_FULL + i), 1);
       mbar_init(BAR(K_EMPTY + i), 2);
@@ -139,6 +160,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(BAR(V_EMPTY + i), 2);
     }
     for (int t = 0; t < 2; ++t) {
+      mbar_init(BAR(Q_FULL + t), 1);
+      mbar_init(BAR(Q_EMPTY + t), 1);
+      mbar_init(BAR(O_FREE + t), 256);
       mbar_init(BAR(S_FULL + t), 1);
       mbar_init(BAR(P_FULL + t), 256);
       mbar_init(BAR(O_FULL + t), 1);
@@ -155,6 +179,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+#ifdef FCSA_WATCHDOG
+  if (threadIdx.x == 0 && blockIdx.x == 0) printf("barrier 0 at smem 0x%x (8 bytes each)\n", bar0);
+#endif
   pdl_wait();          // q, k (normalised by the previous kernel), v, mask are read from here on
 
   if (warp >= 16) reg_dealloc<64>();      // 4 x 104 + 64 = 5 x 96: the pool is what the CTA was launched with
@@ -163,24 +190,32 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // (elect_one, not lane == 0: ptxas then keeps descriptors/addresses in uniform registers
     //  instead of wrapping every UTMALDG/UTCHMMA in a divergence "waterfall" loop)
     if (elect_one()) {
-      mbar_expect_tx(BAR(Q_FULL), 2 * TILE);
+      int g = 0;                                  // key tiles loaded so far (ring position)
+      for (int k = 0;; ++k) {
+        const int idx = item_index(k);
+        if (idx < 0) break;
+        const Item it = load_item(idx);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t) {
+          if (k > 0) mbar_wait(BAR(Q_EMPTY + t), (k - 1) & 1);   // the previous item's last S_t has completed
+          mbar_expect_tx(BAR(Q_FULL + t), TILE);
 #pragma unroll
-        for (int ch = 0; ch < DCH; ++ch)
-          tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL), ch * 64, m0 + 128 * t, h, b);
-      for (int j = 0; j < NT; ++j) {
-        const int ks = j % KS, vs = j % VS;
-        mbar_wait(BAR(K_EMPTY + ks), ((j / KS) & 1) ^ 1);
-        mbar_expect_tx(BAR(K_FULL + ks), TILE);
+          for (int ch = 0; ch < DCH; ++ch)
+            tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL + t), ch * 64, it.m0 + 128 * t, it.h, it.b);
+        }
+        for (int j = 0; j < it.NT; ++j, ++g) {
+          const int ks = g % KS, vs = g % VS;
+          mbar_wait(BAR(K_EMPTY + ks), ((g / KS) & 1) ^ 1);
+          mbar_expect_tx(BAR(K_FULL + ks), TILE);
 #pragma unroll
-        for (int ch = 0; ch < DCH; ++ch)
-          tma_load_4d(sK + ks * TILE + ch * 16384, &tm_k, BAR(K_FULL + ks), ch * 64, j * 128, hk, b);
-        mbar_wait(BAR(V_EMPTY + vs), ((j / VS) & 1) ^ 1);
-        mbar_expect_tx(BAR(V_FULL + vs), TILE);
+          for (int ch = 0; ch < DCH; ++ch)
+            tma_load_4d(sK + ks * TILE + ch * 16384, &tm_k, BAR(K_FULL + ks), ch * 64, j * 128, it.hk, it.b);
+          mbar_wait(BAR(V_EMPTY + vs), ((g / VS) & 1) ^ 1);
+          mbar_expect_tx(BAR(V_FULL + vs), TILE);
 #pragma unroll
-        for (int ch = 0; ch < DCH; ++ch)
-          tma_load_4d(sV + vs * TILE + ch * 16384, &tm_v, BAR(V_FULL + vs), ch * 64, j * 128, hk, b);
+          for (int ch = 0; ch < DCH; ++ch)
+            tma_load_4d(sV + vs * TILE + ch * 16384, &tm_v, BAR(V_FULL + vs), ch * 64, j * 128, it.hk, it.b);
+        }
       }
     }
   } else if (warp == 17 || warp == 18) {
@@ -190,68 +225,89 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // so neither tile ever waits behind the other's barriers; the tensor pipe interleaves the two
     // instruction streams.  K / V ring slots are released by both (barrier count 2).
     const int t = warp - 17;
-    if (NT > 0 && elect_one()) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc<T>(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc<T>(128, D, 0, 1);
-      const int nt = n_t[t];
-      auto issue_S = [&](int j) {
-        const int ks = j % KS;
-        mbar_wait(BAR(K_FULL + ks), (j / KS) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t o = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tmem + t * 128, umma_desc_sw128(sQ + t * TILE + o, 16, 1024),
-                  umma_desc_sw128(sK + ks * TILE + o, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        }
-        umma_commit(BAR(S_FULL + t));
-        umma_commit(BAR(K_EMPTY + ks));          // this tile's share of the release of K_j
-      };
-      if (nt > 0) {
-        mbar_wait(BAR(Q_FULL), 0);
-        tc_fence_after();
-        // The two softmax warpgroups share the MUFU pipe: started half a tile apart, one computes at
-        // full rate while the other is in its per-tile overhead (TMEM load/store, barriers).
-#ifndef FCSA_FWD_NO_STAGGER
-        if (t == 1 && n_t[0] > 0) mbar_wait(BAR(P_FULL + 0), 0);
-#endif
-        issue_S(0);
-      }
-      for (int j = 0; j < NT; ++j) {
-        const int vs = j % VS;
-        if (j < nt) {
-          if (PSEP && j + 1 < nt) {
-            mbar_wait(BAR(S_FREE + t), j & 1);   // S_t(j) sits in registers: produce S_t(j+1) now
-            FCSA_TR(0, j, t);
-            tc_fence_after();
-            issue_S(j + 1);
-          }
-          mbar_wait(BAR(P_FULL + t), j & 1);
-          FCSA_TR(0, j, 2 + 2 * t);
-          mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
+      int g = 0;                                  // ring position of the item's first key tile
+      int c = 0;                                  // iterations of THIS tile so far (parity of its S / P hand-shakes)
+      for (int k = 0;; ++k) {
+        const int idx = item_index(k);
+        if (idx < 0) break;
+        const Item it = load_item(idx);
+        const int nt = t ? it.n_t[1] : it.n_t[0], NT = it.NT;
+        // gj = ring position of key tile j of this item; `last`: no further S_t in this item -> Q_t may be replaced
+        auto issue_S = [&](int gj, bool last) {
+          const int ks = gj % KS;
+          mbar_wait(BAR(K_FULL + ks), (gj / KS) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            umma_ts(tmem + 256 + t * D, tmem + (PSEP ? 384 + t * 64 : t * 128 + 64) + k * 8,
-                    umma_desc_sw128(sV + vs * TILE + k * 2048, 16384, 1024), idesc_o,
-                    (j > 0 || k > 0) ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t o = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_ss(tmem + t * 128, umma_desc_sw128(sQ + t * TILE + o, 16, 1024),
+                    umma_desc_sw128(sK + ks * TILE + o, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
           }
-          umma_commit(BAR(V_EMPTY + vs));
-          if (PSEP) umma_commit(BAR(P_FREE + t));
-          if (j + 1 < nt) {
-            if (!PSEP) issue_S(j + 1);           // P_t aliases S_t: S_t(j+1) goes behind P_t(j) V_j
-          } else {
-            umma_commit(BAR(O_FULL + t));
-          }
+          umma_commit(BAR(S_FULL + t));
+          umma_commit(BAR(K_EMPTY + ks));          // this tile's share of the release of K_j
+          if (last) umma_commit(BAR(Q_EMPTY + t));
+        };
+        if (nt > 0) {
+          mbar_wait(BAR(Q_FULL + t), k & 1);
+          // PSEP: S_t of the previous item's last iteration must sit in registers before it is overwritten
+          // (!PSEP: this S goes behind the previous P_t V in the in-order pipe, and P_FULL implied the reads)
+          if (PSEP && c > 0) mbar_wait(BAR(S_FREE + t), (c - 1) & 1);
+          tc_fence_after();
+          // The two softmax warpgroups share the MUFU pipe: started half a tile apart, one computes at
+          // full rate while the other is in its per-tile overhead (TMEM load/store, barriers).
+#ifndef FCSA_FWD_NO_STAGGER
+          if (k == 0 && t == 1 && it.n_t[0] > 0) mbar_wait(BAR(P_FULL + 0), 0);
+#endif
+          issue_S(g, nt == 1);
         } else {
-          // this tile has no work on key tile j (causal: tile 0 ends one key tile before tile 1;
-          // or the tile is past the end of q): still release the ring slots the other tile uses
-          // (paced by the fills: one arrival per refill of the slot, never two in one phase)
-          mbar_wait(BAR(K_FULL + j % KS), (j / KS) & 1);
-          mbar_arrive(BAR(K_EMPTY + j % KS));
-          mbar_wait(BAR(V_FULL + vs), (j / VS) & 1);
-          mbar_arrive(BAR(V_EMPTY + vs));
+          // nothing to compute for this tile: keep its per-item phases moving, in step with the producer
+          // (an issuer running two items ahead would alias the parity the producer waits for)
+          mbar_wait(BAR(Q_FULL + t), k & 1);
+          mbar_arrive(BAR(Q_EMPTY + t));
+          mbar_arrive(BAR(O_FULL + t));
         }
+        for (int j = 0; j < NT; ++j) {
+          const int vs = (g + j) % VS;
+          if (j < nt) {
+            if (PSEP && j + 1 < nt) {
+              mbar_wait(BAR(S_FREE + t), c & 1);   // S_t(j) sits in registers: produce S_t(j+1) now
+              FCSA_TR(0, j, t);
+              tc_fence_after();
+              issue_S(g + j + 1, j + 2 == nt);
+            }
+            mbar_wait(BAR(P_FULL + t), c & 1);
+            FCSA_TR(0, j, 2 + 2 * t);
+            if (j == 0 && k > 0) mbar_wait(BAR(O_FREE + t), (k - 1) & 1);   // the previous item's O_t has been read out
+            mbar_wait(BAR(V_FULL + vs), ((g + j) / VS) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              umma_ts(tmem + 256 + t * D, tmem + (PSEP ? 384 + t * 64 : t * 128 + 64) + kk * 8,
+                      umma_desc_sw128(sV + vs * TILE + kk * 2048, 16384, 1024), idesc_o,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(BAR(V_EMPTY + vs));
+            if (PSEP) umma_commit(BAR(P_FREE + t));
+            if (j + 1 < nt) {
+              if (!PSEP) issue_S(g + j + 1, j + 2 == nt);   // P_t aliases S_t: S_t(j+1) goes behind P_t(j) V_j
+            } else {
+              umma_commit(BAR(O_FULL + t));
+            }
+            ++c;
+          } else {
+            // this tile has no work on key tile j (causal: tile 0 ends one key tile before tile 1;
+            // or the tile is past the end of q): still release the ring slots the other tile uses
+            // (paced by the fills: one arrival per refill of the slot, never two in one phase)
+            mbar_wait(BAR(K_FULL + (g + j) % KS), ((g + j) / KS) & 1);
+            mbar_arrive(BAR(K_EMPTY + (g + j) % KS));
+            mbar_wait(BAR(V_FULL + vs), ((g + j) / VS) & 1);
+            mbar_arrive(BAR(V_EMPTY + vs));
+          }
+        }
+        g += NT;
       }
     }
   } else if (warp < 16) {
@@ -261,17 +317,23 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int half = (warp >> 2) & 1;        // which 64 of the 128 key columns of every tile
     const int wq = warp & 3;                 // TMEM lane quarter this warp may touch
     const int r = wq * 32 + lane;            // row inside the tile
-    const int row_g = m0 + 128 * t + r;      // global query row
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t tS = lane_base + t * 128 + 64 * half;
     const uint32_t tP = (PSEP ? lane_base + 384 + t * 64 : lane_base + t * 128 + 64) + 32 * half;
     const uint32_t tO = lane_base + 256 + t * D;
-    const int nt = n_t[t];
     float nc2 = -a.c2;
     if constexpr (BIAS) {
       if (a.bias_amax != nullptr) nc2 -= fmaxf(__ldg(a.bias_amax), 0.f) * 1.4426950408889634f;
     }
     const float c1 = a.c1;
+    const bool tr_lane = (half == 0 && wq == 0 && lane == 0);
+    int cc = 0;                              // iterations of this tile so far, over all items (barrier parities)
+    for (int k = 0;; ++k) {
+    const int idx = item_index(k);
+    if (idx < 0) break;
+    const Item it = load_item(idx);
+    const int b = it.b, h = it.h, m0 = it.m0, nt = t ? it.n_t[1] : it.n_t[0];
+    const int row_g = m0 + 128 * t + r;      // global query row
     // bias row of this query (clamped for the padding rows of the last tile, which are never stored)
     const T* brow = nullptr;
     if constexpr (BIAS)
@@ -295,10 +357,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float l = 0.f;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // two partial row-sum chains
 
-    const bool tr_lane = (half == 0 && wq == 0 && lane == 0);
-    for (int j = 0; j < nt; ++j) {
+    for (int j = 0; j < nt; ++j, ++cc) {
       if (tr_lane) FCSA_TR(1 + t, j, 0);
-      mbar_wait(BAR(S_FULL + t), j & 1);
+      mbar_wait(BAR(S_FULL + t), cc & 1);
       if (tr_lane) FCSA_TR(1 + t, j, 1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
@@ -315,9 +376,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // Waited for as late as possible - after the first chunk of exps - so it rarely costs anything.
       auto p_cols_free = [&]() {
         if (PSEP) {
-          if (j > 0) mbar_wait(BAR(P_FREE + t), (j - 1) & 1);
+          if (cc > 0) mbar_wait(BAR(P_FREE + t), (cc - 1) & 1);
         } else {
-          mbar_wait(BAR(S_FREE + t), j & 1);
+          mbar_wait(BAR(S_FREE + t), cc & 1);
         }
       };
       if (tr_lane) FCSA_TR(1 + t, j, 3);
@@ -404,7 +465,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // O == 0 -> o = 0; reference: cu:1239 uses 1e-10, too large here because shift = scale*groups
     // makes legitimately tiny row sums).
     l += (l2a.x + l2a.y) + (l2b.x + l2b.y);
-    float* lbuf = reinterpret_cast<float*>(smem + Cfg::kOffL) + t * 256;
+    float* lbuf = reinterpret_cast<float*>(smem + Cfg::kOffL) + (k & 1) * 512 + t * 256;   // double-buffered over items
     lbuf[half * 128 + r] = l;
     named_bar_sync(1 + t, 256);
     l += lbuf[(half ^ 1) * 128 + r];
@@ -415,15 +476,19 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float* orow32 = reinterpret_cast<float*>(a.o) + o_off;
     const bool o_f32 = a.o_f32 != 0;
     constexpr int CPH = D / 64;              // 32-column chunks of O per half
+    mbar_wait(BAR(O_FULL + t), k & 1);
     if (nt > 0) {
-      mbar_wait(BAR(O_FULL + t), 0);
       tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < CPH; ++cc) {
-        const int c = half * CPH + cc;
+      for (int ch = 0; ch < CPH; ++ch) {
+        const int c = half * CPH + ch;
         uint32_t acc[32];
         tmem_ld_x32(tO + c * 32, acc);
         tmem_ld_wait();
+        if (ch == CPH - 1) {                   // O_t is in registers: the next item's first P_t V may overwrite it
+          tc_fence_before();
+          mbar_arrive(BAR(O_FREE + t));
+        }
         if (row_ok && o_f32) {
 #pragma unroll
           for (int v = 0; v < 8; ++v)
@@ -442,17 +507,21 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
-    } else if (row_ok && o_f32) {
+    } else {
+      mbar_arrive(BAR(O_FREE + t));
+      if (row_ok && o_f32) {
 #pragma unroll
-      for (int v = 0; v < D / 8; ++v)
-        *reinterpret_cast<float4*>(orow32 + half * (D / 2) + v * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else if (row_ok) {
+        for (int v = 0; v < D / 8; ++v)
+          *reinterpret_cast<float4*>(orow32 + half * (D / 2) + v * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (row_ok) {
 #pragma unroll
-      for (int v = 0; v < D / 16; ++v)
-        *reinterpret_cast<uint4*>(orow + half * (D / 2) + v * 8) = make_uint4(0, 0, 0, 0);
+        for (int v = 0; v < D / 16; ++v)
+          *reinterpret_cast<uint4*>(orow + half * (D / 2) + v * 8) = make_uint4(0, 0, 0, 0);
+      }
     }
     if (half == 0 && row_ok && a.inv_l != nullptr)
       a.inv_l[((long long)b * a.H + h) * a.Nq + row_g] = inv;
+    }   // items
   }
 
   // ---- teardown ------------------------------------------------------------------------

@@ -29,6 +29,28 @@ __device__ long long g_fcsa_trace[8][48][8];
 #define FCSA_TR(role, it, slot) do { } while (0)
 #endif
 
+// Per-CTA timeline (test builds only, -DFCSA_CTA_TIMELINE): clock64 of up to 8 events per CTA plus the SM id,
+// to see how consecutive CTAs of one SM follow each other.
+#ifdef FCSA_CTA_TIMELINE
+__device__ long long g_fcsa_cta_t[4096][10];
+#define FCSA_CTA_T(cond, slot)                                                        \
+  do {                                                                                \
+    if ((cond) && blockIdx.x < 4096) {                                                \
+      g_fcsa_cta_t[blockIdx.x][slot] = clock64();                                     \
+      if ((slot) == 0) {                                                              \
+        unsigned smid_;                                                               \
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                            \
+        g_fcsa_cta_t[blockIdx.x][8] = smid_;                                          \
+        unsigned long long gt_;                                                       \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                       \
+        g_fcsa_cta_t[blockIdx.x][9] = (long long)gt_;                                 \
+      }                                                                               \
+    }                                                                                 \
+  } while (0)
+#else
+#define FCSA_CTA_T(cond, slot) do { } while (0)
+#endif
+
 namespace fcsa {
 
 // ----------------------------------------------------------------------------------
@@ -97,8 +119,19 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 // Spin until the phase with the given parity has completed.  try_wait itself suspends
 // the thread for a hardware-defined interval, so this is not a hot spin.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef FCSA_WATCHDOG
+  // debug builds: report the barrier a thread is stuck on (shared-memory address) and stop the kernel
+  const long long t_start = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t_start > 2000000000LL) {
+      printf("stuck: block %d thread %d barrier smem 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (UMMA/TMA)

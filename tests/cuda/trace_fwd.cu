@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <vector>
 
 #include "../../flash_cosine_sim_attention_b200/csrc/fwd_kernel.cuh"
 #include "../../flash_cosine_sim_attention_b200/csrc/tensor_map.h"
@@ -24,6 +26,7 @@ int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 4, H = argc > 2 ? atoi(argv[2]) : 8, D = 64;
   const int Nq = argc > 3 ? atoi(argv[3]) : 4096, Nk = argc > 4 ? atoi(argv[4]) : 4096;
   const int causal = argc > 5 ? atoi(argv[5]) : 1;
+  const int grid_arg = argc > 6 ? atoi(argv[6]) : 148;    // CTAs (persistent); 0 = one CTA per work item
   const int N = Nq > Nk ? Nq : Nk;
   const size_t n = (size_t)B * H * N * D;
   __nv_bfloat16 *q, *k, *v, *o;
@@ -56,13 +59,69 @@ int main(int argc, char** argv) {
   float best = 1e9f;
   for (int rep = 0; rep < reps; ++rep) {
     CK(cudaEventRecord(e0));
-    kern<<<a.n_qblk * B * H, Cfg::kThreads, Cfg::kSmem>>>(tq, tk, tv, a);
+    const int items = a.n_qblk * B * H;
+    kern<<<(grid_arg > 0 && grid_arg < items) ? grid_arg : items, Cfg::kThreads, Cfg::kSmem>>>(tq, tk, tv, a);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     if (ms < best) best = ms;
   }
-  printf("B %d H %d Nq %d Nk %d causal %d: fwd kernel best of %d: %.1f us\n", B, H, Nq, Nk, causal, reps, best * 1e3);
+  printf("B %d H %d Nq %d Nk %d causal %d grid %d: fwd kernel best of %d: %.1f us\n", B, H, Nq, Nk, causal, grid_arg, reps, best * 1e3);
+  if (argc > 7) {
+    // sustained: N launches back to back (no host synchronisation in between), average time per launch
+    const int nrun = atoi(argv[7]);
+    const int items = a.n_qblk * B * H;
+    const int grid = (grid_arg > 0 && grid_arg < items) ? grid_arg : items;
+    for (int pass = 0; pass < 3; ++pass) {
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < nrun; ++i) kern<<<grid, Cfg::kThreads, Cfg::kSmem>>>(tq, tk, tv, a);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      printf("  sustained pass %d: %d launches back to back: %.1f us per launch\n", pass, nrun, ms * 1e3 / nrun);
+    }
+  }
+#ifdef FCSA_CTA_TIMELINE
+  {
+    // per SM: the CTAs it ran, in start order; columns relative to the SM's first CTA start
+    const int nblk = a.n_qblk * B * H;
+    static long long ct[4096][10];
+    CK(cudaMemcpyFromSymbol(ct, g_fcsa_cta_t, sizeof(ct)));
+    printf("slots: 0 entry, 1 setup done, 2/3 tile0/1 second iteration top, 4/5 tile0/1 loop end, 6 tile1 epilogue done, 7 exit\n");
+    for (int sm = 0; sm < 3; ++sm) {
+      std::vector<int> ids;
+      for (int i = 0; i < nblk && i < 4096; ++i) if (ct[i][8] == sm) ids.push_back(i);
+      std::sort(ids.begin(), ids.end(), [&](int x, int y) { return ct[x][0] < ct[y][0]; });
+      if (ids.empty()) continue;
+      const long long t0 = ct[ids[0]][0];
+      long long prev_exit = t0;
+      for (int id : ids) {
+        printf("sm %d cta %4d (qblk rank %3d): gap %6lld |", sm, id, id / (B * H), ct[id][0] - prev_exit);
+        for (int s2 = 0; s2 < 8; ++s2) printf(" %7lld", ct[id][s2] - ct[id][0]);
+        printf("\n");
+        prev_exit = ct[id][7];
+      }
+    }
+    // totals over all SMs
+    double gap = 0, setup = 0, body = 0, epi = 0, exitt = 0; int n = 0, ngap = 0;
+    for (int sm = 0; sm < 148; ++sm) {
+      std::vector<int> ids;
+      for (int i = 0; i < nblk && i < 4096; ++i) if (ct[i][8] == sm) ids.push_back(i);
+      std::sort(ids.begin(), ids.end(), [&](int x, int y) { return ct[x][0] < ct[y][0]; });
+      for (size_t k2 = 0; k2 < ids.size(); ++k2) {
+        const int id = ids[k2];
+        if (k2 > 0) { gap += ct[id][0] - ct[ids[k2 - 1]][7]; ++ngap; }
+        setup += ct[id][1] - ct[id][0];
+        epi += ct[id][6] - ct[id][5];
+        exitt += ct[id][7] - ct[id][6];
+        body += ct[id][5] - ct[id][1];
+        ++n;
+      }
+    }
+    printf("mean per CTA (cycles): launch gap %.0f, setup %.0f, body(setup..tile1 loop end) %.0f, tile1 epilogue %.0f, exit %.0f  (%d CTAs)\n",
+           gap / (ngap ? ngap : 1), setup / n, body / n, epi / n, exitt / n, n);
+  }
+#endif
 #ifdef FCSA_TRACE
   static long long tr[8][48][8];
   CK(cudaMemcpyFromSymbol(tr, g_fcsa_trace, sizeof(tr)));
