@@ -439,6 +439,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = warp >> 2;
+  FCSA_CTA_T(threadIdx.x == 0, 0);
   pdl_launch_dependents();
 
   // ---- work item --------------------------------------------------------------------------
@@ -490,6 +491,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();          // slivers / stats come from the preprocess kernel; accumulators are zero on entry
+  FCSA_CTA_T(threadIdx.x == 0, 1);
 
   if (wg == 4) {
     reg_dealloc<64>();
@@ -810,6 +812,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // c3 / delta of this tile are in smem
         mbar_wait(BAR(S_FULL), i & 1);
         if (tr_lane) FCSA_TR(1, i, 1);
+        if (i == 0) FCSA_CTA_T(tr_lane, 2);
         tc_fence_after();
         // ---- exp stage.  The shared-memory operands are fetched in one batch so the exp chain
         // (FFMA -> MUFU -> pack) of CW independent elements can be pipelined freely.  The masked
@@ -929,6 +932,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         mbar_arrive(BAR(DS_FULL));
         if (tr_lane) FCSA_TR(2, i, 3);
+        if (i == 0) FCSA_CTA_T(tr_lane, 3);
+        if (i == NI - 1) FCSA_CTA_T(tr_lane, 4);
         if (i > 0) reduce_dq(i - 1);
       }
       if (NI > 0) {
@@ -938,6 +943,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       if (lane == 0) bulk_wait_group<0>();
       __syncwarp();
+      FCSA_CTA_T(tr_lane, 5);
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
@@ -1049,8 +1055,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 
   tc_fence_before();
+  FCSA_CTA_T(threadIdx.x == 0, 6);
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem, 512);
+  FCSA_CTA_T(threadIdx.x == 32 * 17, 7);
 }
 
 // ------------------------------------------------------------------------------------------

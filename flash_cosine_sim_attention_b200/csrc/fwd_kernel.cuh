@@ -28,6 +28,12 @@
 
 #include "sm100_primitives.cuh"
 
+#ifndef FCSA_FWD_SWAP
+// 1: the two tile engines of a CTA swap the upper / lower 128 rows from item to item.  Causal: the upper rows
+// see one key tile fewer, so a fixed assignment lets one engine run ahead by one iteration per item until the
+// shared K/V ring stops it; alternating keeps the two within one iteration of each other.
+#define FCSA_FWD_SWAP 1
+#endif
 #ifndef FCSA_POLY_EVERY
 #define FCSA_POLY_EVERY 4   // forward, D = 64: 1 of every N exp pairs runs on the FMA pipe (0 = none)
 #endif
@@ -201,7 +207,8 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_expect_tx(BAR(Q_FULL + t), TILE);
 #pragma unroll
           for (int ch = 0; ch < DCH; ++ch)
-            tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL + t), ch * 64, it.m0 + 128 * t, it.h, it.b);
+            tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL + t), ch * 64, it.m0 + 128 * (t ^ (k & FCSA_FWD_SWAP)),
+                        it.h, it.b);
         }
         for (int j = 0; j < it.NT; ++j, ++g) {
           const int ks = g % KS, vs = g % VS;
@@ -234,7 +241,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int idx = item_index(k);
         if (idx < 0) break;
         const Item it = load_item(idx);
-        const int nt = t ? it.n_t[1] : it.n_t[0], NT = it.NT;
+        const int nt = (t ^ (k & FCSA_FWD_SWAP)) ? it.n_t[1] : it.n_t[0], NT = it.NT;
         // gj = ring position of key tile j of this item; `last`: no further S_t in this item -> Q_t may be replaced
         auto issue_S = [&](int gj, bool last) {
           const int ks = gj % KS;
@@ -332,8 +339,9 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int idx = item_index(k);
     if (idx < 0) break;
     const Item it = load_item(idx);
-    const int b = it.b, h = it.h, m0 = it.m0, nt = t ? it.n_t[1] : it.n_t[0];
-    const int row_g = m0 + 128 * t + r;      // global query row
+    const int tl = t ^ (k & FCSA_FWD_SWAP);  // which 128 rows of the item this tile engine takes (see FCSA_FWD_SWAP)
+    const int b = it.b, h = it.h, m0 = it.m0, nt = tl ? it.n_t[1] : it.n_t[0];
+    const int row_g = m0 + 128 * tl + r;     // global query row
     // bias row of this query (clamped for the padding rows of the last tile, which are never stored)
     const T* brow = nullptr;
     if constexpr (BIAS)
@@ -385,7 +393,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
       const int col0 = j * 128;
       const bool need_mask = a.has_mask || (col0 + 127 >= a.Nk) ||
-                             (a.causal && (col0 + 127 > m0 + 128 * t + off));
+                             (a.causal && (col0 + 127 > m0 + 128 * tl + off));
       if (!need_mask) {
         // packed f32x2 math: one FFMA2 / FADD2 per element pair (halves the FMA-pipe instruction
         // count next to the MUFU-bound exps); two independent row-sum chains per thread
