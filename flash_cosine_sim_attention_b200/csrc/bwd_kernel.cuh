@@ -41,6 +41,8 @@
 // (fp32 reductions), reference cu:1474-1476 / 1574-1576.
 #pragma once
 
+#include <stdlib.h>
+#include <algorithm>
 #include <type_traits>
 
 #ifndef FCSA_BWD_POLY_EVERY
@@ -417,8 +419,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  const uint32_t sK = smem_u32(smem + Cfg::kOffK);
-  const uint32_t sV = smem_u32(smem + Cfg::kOffV);
+  // two 128 x D operand buffers: item n keeps K in buffer (n & 1) and V in the other one.  D = 64: V only
+  // passes through shared memory on its way to TMEM, so the next item's K is prefetched into it; the next
+  // item's V follows into K's buffer when the last dQ MMA and the dK epilogue are done with it.
+  const uint32_t sKV0 = smem_u32(smem + Cfg::kOffK);
+  auto buf_k = [&](int n) { return sKV0 + ((n & 1) ? Cfg::kKV : 0); };
+  auto buf_v = [&](int n) { return sKV0 + ((n & 1) ? 0 : Cfg::kKV); };
   const uint32_t sQ = smem_u32(smem + Cfg::kOffQ);
   const uint32_t sDO = smem_u32(smem + Cfg::kOffDO);
   const uint32_t sDS = smem_u32(smem + Cfg::kOffDS);
@@ -430,9 +436,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   enum {
-    KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
-    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, KV_TMEM, DS_FULL,
-    DQ_FULL, DKV_FULL, NBARS
+    K_FULL = 0, V_FULL = 1, Q_FULL = 2, Q_EMPTY = Q_FULL + NST, DO_FULL = Q_EMPTY + NST, DO_EMPTY = DO_FULL + NST,
+    S_FULL = DO_EMPTY + NST, S_FREE, P_FULL, PV_DONE, DP_FULL, K_TMEM, V_TMEM, DS_FULL,
+    DQ_FULL, DKV_FULL, DV_FREE, DK_FREE, KS_FREE, NBARS
   };
   static_assert(NBARS * 8 + 4 <= 256, "barrier area");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
@@ -442,21 +448,41 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   FCSA_CTA_T(threadIdx.x == 0, 0);
   pdl_launch_dependents();
 
-  // ---- work item --------------------------------------------------------------------------
+  // ---- work items -------------------------------------------------------------------------
+  // One item = one 128-key tile of one (batch, head) with all the query tiles that can see it.  Items are
+  // numbered heaviest first (causal: the first key tiles are seen by the most queries) and dealt to the CTAs
+  // in snake order.  A grid of one CTA per SM makes the CTA persistent (D = 64): TMEM, barriers and the
+  // Q / dO ring live on across items, the stream of query tiles is continuous (the dQ tile of an item's last
+  // query tile is drained under the next item's first one), the next item's K is prefetched, and the dK / dV
+  // epilogue of one item overlaps the first MMAs of the next.  A grid of n_items CTAs = one item per CTA.
   const int bh_count = a.B * a.H;
-  const int jt = blockIdx.x / bh_count;                 // key tile; ascending = heaviest first (causal)
-  const int bh = blockIdx.x - jt * bh_count;
-  const int b = bh / a.H, h = bh - b * a.H;
-  const int hk = (a.kv_heads == 1) ? 0 : h;
+  const int n_items = ((a.Nk + 127) >> 7) * bh_count;
   const int off = a.Nk - a.Nq;
-  const int key0 = jt * 128;
-  int i_lo = 0;
-  if (a.causal) {
-    // first query tile with a row that can see key0: QT*i + QT-1 + off >= key0
-    const int x = key0 - off - (QT - 1);
-    i_lo = x <= 0 ? 0 : (x + QT - 1) / QT;
-  }
-  const int NI = a.nqt - i_lo;                          // number of query tiles to visit (>= 1)
+  struct Item {
+    int b, h, hk, bh, key0, i_lo, NI;
+  };
+  auto item_index = [&](int r) -> int {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int idx = r * G + ((r & 1) ? (G - 1 - c) : c);
+    return idx < n_items ? idx : -1;
+  };
+  auto load_item = [&](int idx) -> Item {
+    Item it;
+    const int jt = idx / bh_count;                  // key tile; ascending = heaviest first (causal)
+    it.bh = idx - jt * bh_count;
+    it.b = it.bh / a.H;
+    it.h = it.bh - it.b * a.H;
+    it.hk = (a.kv_heads == 1) ? 0 : it.h;
+    it.key0 = jt * 128;
+    it.i_lo = 0;
+    if (a.causal) {
+      // first query tile with a row that can see key0: QT*i + QT-1 + off >= key0
+      const int x = it.key0 - off - (QT - 1);
+      it.i_lo = x <= 0 ? 0 : (x + QT - 1) / QT;
+    }
+    it.NI = a.nqt - it.i_lo;                        // number of query tiles to visit (>= 1)
+    return it;
+  };
 
   // ---- setup ------------------------------------------------------------------------------
   if (warp == 16 && elect_one()) {
@@ -464,7 +490,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
-    mbar_init(BAR(KV_FULL), 1);
+    mbar_init(BAR(K_FULL), 1);
+    mbar_init(BAR(V_FULL), 1);
     for (int s = 0; s < NST; ++s) {
       mbar_init(BAR(Q_FULL + s), 1);
       mbar_init(BAR(Q_EMPTY + s), 2);
@@ -478,8 +505,12 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(BAR(DP_FULL), 1);
     mbar_init(BAR(DS_FULL), 512);
     mbar_init(BAR(DQ_FULL), 1);
-    mbar_init(BAR(KV_TMEM), 256);
+    mbar_init(BAR(K_TMEM), 128);
+    mbar_init(BAR(V_TMEM), 128);
     mbar_init(BAR(DKV_FULL), 2);
+    mbar_init(BAR(DV_FREE), 128);       // dV / dK accumulators read out by the epilogue warpgroups
+    mbar_init(BAR(DK_FREE), 128);
+    mbar_init(BAR(KS_FREE), 129);       // K's shared-memory buffer: last dQ MMA (commit) + the dK epilogue warps
     fence_mbar_init();
   }
   if (warp == 17) {
@@ -495,70 +526,72 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (wg == 4) {
     reg_dealloc<64>();
-#ifdef FCSA_TRACE
-    if (warp == 19 && lane == 0 && blockIdx.x == FCSA_TRACE_CTA) {
-      // passive observer: when do the tensor-pipe results become visible?  (bounded spins: an
-      // observer that falls two phases behind must not hang the kernel)
-      auto watch = [&](int bar, uint32_t par) {
-        for (int tries = 0; tries < (1 << 14); ++tries)
-          if (mbar_try_wait(BAR(bar), par)) return;
-      };
-      for (int i = 0; i < NI; ++i) {
-        watch(S_FULL, i & 1);
-        FCSA_TR(5, i, 0);
-        watch(DP_FULL, i & 1);
-        FCSA_TR(5, i, 1);
-        watch(PV_DONE, i & 1);
-        FCSA_TR(5, i, 2);
-        watch(DQ_FULL, i & 1);
-        FCSA_TR(5, i, 3);
-      }
-    }
-#endif
-    if (warp == 16) {
-      // =============================== TMA producer ===============================
-      if (NI > 0 && elect_one()) {
-        mbar_expect_tx(BAR(KV_FULL), 2 * Cfg::kKV + (AUG ? 4096 : 0));
+    if (warp == 19) {
+      // =============================== K / V producer ==============================
+      // (a thread of its own: its waits - V copied to TMEM, K's buffer released - must not hold up the ring)
+      if (elect_one()) {
+        for (int n = 0;; ++n) {
+          const int idx = item_index(n);
+          if (idx < 0) break;
+          const Item it = load_item(idx);
+          if (n > 0) {
+            mbar_wait(BAR(V_TMEM), (n - 1) & 1);      // buf_k(n) held V(n-1): copied to TMEM
+            mbar_wait(BAR(K_TMEM), (n - 1) & 1);      // K(n-1) has landed and K_FULL's only waiters are past it:
+          }                                           // the barrier may be re-armed
+          mbar_expect_tx(BAR(K_FULL), Cfg::kKV + ((AUG && n == 0) ? 4096 : 0));
 #pragma unroll
-        for (int ch = 0; ch < KCH; ++ch) {
-          tma_load_4d(sK + ch * 16384, &tm_k, BAR(KV_FULL), ch * 64, key0, hk, b);
-          tma_load_4d(sV + ch * 16384, &tm_v, BAR(KV_FULL), ch * 64, key0, hk, b);
-        }
-        if constexpr (AUG) tma_load_4d(sOnes, &tm_ones, BAR(KV_FULL), 0, 0, 0, 0);
-        for (int i = 0; i < NI; ++i) {
-          const int st = i % NST, qt = i_lo + i;
-          const uint32_t par = ((i / NST) & 1) ^ 1;
-          mbar_wait(BAR(Q_EMPTY + st), par);
-          FCSA_TR(4, i, 0);
-          mbar_expect_tx(BAR(Q_FULL + st), Cfg::kQ + (AUG ? Cfg::kSliver : 8 * QT));
+          for (int ch = 0; ch < KCH; ++ch) tma_load_4d(buf_k(n) + ch * 16384, &tm_k, BAR(K_FULL), ch * 64, it.key0, it.hk, it.b);
+          if constexpr (AUG) {
+            if (n == 0) tma_load_4d(sOnes, &tm_ones, BAR(K_FULL), 0, 0, 0, 0);
+          }
+          if (n > 0) mbar_wait(BAR(KS_FREE), (n - 1) & 1);       // buf_v(n) held K(n-1): dQ MMAs and dK epilogue done
+          mbar_expect_tx(BAR(V_FULL), Cfg::kKV);
 #pragma unroll
-          for (int ch = 0; ch < KCH; ++ch)
-            tma_load_4d(sQ + st * Cfg::kQ + ch * QCHUNK, &tm_q, BAR(Q_FULL + st), ch * 64, qt * QT, h, b);
-          if constexpr (AUG)
-            tma_load_4d(sAug + st * 2 * Cfg::kSliver, &tm_aug, BAR(Q_FULL + st), 0, qt * QT, bh, 0);
-          else
-            bulk_load_1d(sStats + st * 1024,
-                         a.stats + ((long long)bh * a.nqt + qt) * 2 * QT, 8 * QT, BAR(Q_FULL + st));
-          mbar_wait(BAR(DO_EMPTY + st), par);
-          FCSA_TR(4, i, 1);
-          mbar_expect_tx(BAR(DO_FULL + st), Cfg::kQ + (AUG ? Cfg::kSliver : 0));
-#pragma unroll
-          for (int ch = 0; ch < KCH; ++ch)
-            tma_load_4d(sDO + st * Cfg::kQ + ch * QCHUNK, &tm_do, BAR(DO_FULL + st), ch * 64, qt * QT, h, b);
-          if constexpr (AUG)
-            tma_load_4d(sAug + st * 2 * Cfg::kSliver + Cfg::kSliver, &tm_aug, BAR(DO_FULL + st), 16, qt * QT, bh, 0);
+          for (int ch = 0; ch < KCH; ++ch) tma_load_4d(buf_v(n) + ch * 16384, &tm_v, BAR(V_FULL), ch * 64, it.key0, it.hk, it.b);
         }
       }
-    } else if (warp == 17 || warp == 18) {
+    } else if (warp == 16) {
+      // =============================== Q / dO ring producer =======================
+      if (elect_one()) {
+        int tq = 0;                                 // query tiles so far, over all items (ring position)
+        for (int n = 0;; ++n) {
+          const int idx = item_index(n);
+          if (idx < 0) break;
+          const Item it = load_item(idx);
+          for (int i = 0; i < it.NI; ++i, ++tq) {
+            const int st = tq % NST, qt = it.i_lo + i;
+            const uint32_t par = ((tq / NST) & 1) ^ 1;
+            mbar_wait(BAR(Q_EMPTY + st), par);
+            if (n == 0) FCSA_TR(4, i, 0);
+            mbar_expect_tx(BAR(Q_FULL + st), Cfg::kQ + (AUG ? Cfg::kSliver : 8 * QT));
+#pragma unroll
+            for (int ch = 0; ch < KCH; ++ch)
+              tma_load_4d(sQ + st * Cfg::kQ + ch * QCHUNK, &tm_q, BAR(Q_FULL + st), ch * 64, qt * QT, it.h, it.b);
+            if constexpr (AUG)
+              tma_load_4d(sAug + st * 2 * Cfg::kSliver, &tm_aug, BAR(Q_FULL + st), 0, qt * QT, it.bh, 0);
+            else
+              bulk_load_1d(sStats + st * 1024,
+                           a.stats + ((long long)it.bh * a.nqt + qt) * 2 * QT, 8 * QT, BAR(Q_FULL + st));
+            mbar_wait(BAR(DO_EMPTY + st), par);
+            if (n == 0) FCSA_TR(4, i, 1);
+            mbar_expect_tx(BAR(DO_FULL + st), Cfg::kQ + (AUG ? Cfg::kSliver : 0));
+#pragma unroll
+            for (int ch = 0; ch < KCH; ++ch)
+              tma_load_4d(sDO + st * Cfg::kQ + ch * QCHUNK, &tm_do, BAR(DO_FULL + st), ch * 64, qt * QT, it.h, it.b);
+            if constexpr (AUG)
+              tma_load_4d(sAug + st * 2 * Cfg::kSliver + Cfg::kSliver, &tm_aug, BAR(DO_FULL + st), 16, qt * QT, it.bh, 0);
+          }
+        }
+      }
+    } else {
       // =============================== MMA issuers ================================
       // Two issuing threads, one per dependency chain, so that neither waits behind the other's
       // barriers (the tensor pipe interleaves the two instruction streams):
-      //   warp 13 (exp side): S^T(i+1) as soon as the exp warpgroup holds S^T(i) in registers;
-      //                       dV(i) += P^T(i) dO(i) when P^T(i) is in the X columns
-      //   warp 14 (dS side) : dK(i) += dS^T(i) Q(i), dP^T(i+1) (it overwrites dS^T(i), so it goes
-      //                       behind dK(i) in the in-order pipe), dQ(i)
+      //   warp 17 (chain A): S^T(i+1) as soon as the compute warps hold S^T(i) in registers;
+      //                      dV(i) += P^T(i) dO(i) when P^T(i) is in place; dP^T(i+1) right behind it
+      //   warp 18 (chain B): dK(i) += dS^T(i) Q(i), then dQ(i)
       // Q / dO ring slots are read by both chains: their empty barriers count 2.
-      if (NI > 0 && elect_one()) {
+      if (elect_one()) {
         constexpr uint32_t idesc_s = umma_idesc<T>(128, QT, 0, 0);    // S^T, dP^T  (A, B K-major)
         constexpr uint32_t idesc_ts = umma_idesc<T>(128, D, 0, 1);    // dV, dK (A from TMEM, B MN-major)
         constexpr uint32_t idesc_dq = umma_idesc<T>(128, 64, 1, 1);   // dQ / dQ^T (A, B MN-major)
@@ -585,7 +618,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const int w = (16 * kk) / CW;
           return static_cast<uint32_t>(w * CW + (16 * kk - w * CW) / 2);
         };
-        // D = 64: K and V also sit in TMEM (the X columns, written once per CTA by the compute warps),
+        // D = 64: K and V also sit in TMEM (the X columns, written once per item by the compute warps),
         // so S^T and dP^T read only their B operand from shared memory
         auto issue_ST_ts = [&](uint32_t d_col, uint32_t a_col, uint32_t b_smem) {
 #pragma unroll
@@ -594,100 +627,120 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128(b_smem + (k >> 2) * QCHUNK + (k & 3) * 32, 16, 1024), idesc_s,
                     k > 0 ? 1u : 0u);
         };
-        // st = ring stage of the Q / dO tile (and of its sliver)
-        auto issue_S = [&](int st) {
-          const uint32_t q_smem = sQ + st * Cfg::kQ;
-          if constexpr (KV_IN_TMEM) issue_ST_ts(TM_S, TM_X, q_smem);
-          else issue_ST(TM_S, sK, q_smem);
-          if constexpr (AUG)      // S^T += ones * (c3/c1)^T : the exponent offset of every query column
-            umma_ss(tmem + TM_S, umma_desc_sw32(sOnes), umma_desc_sw32(sAug + st * 2 * Cfg::kSliver), idesc_s, 1u);
-        };
-        auto issue_dP = [&](int st) {
-          const uint32_t do_smem = sDO + st * Cfg::kQ;
-          if constexpr (KV_IN_TMEM) issue_ST_ts(TM_DP, TM_X + 32, do_smem);
-          else issue_ST(TM_DP, sV, do_smem);
-          if constexpr (AUG)      // dP^T += ones * (-delta)^T
-            umma_ss(tmem + TM_DP, umma_desc_sw32(sOnes),
-                    umma_desc_sw32(sAug + st * 2 * Cfg::kSliver + Cfg::kSliver), idesc_s, 1u);
-        };
-        mbar_wait(BAR(KV_FULL), 0);
+        int tq = 0;                                 // query tiles so far, over all items
         if (warp == 17) {
-          // chain A: everything that does not depend on dS.  S^T(i+1) as soon as S^T(i) is in
-          // registers; dV(i) when P^T(i) is in place; dP^T(i+1) right behind dV(i) (it overwrites
-          // P^T(i): same issuing thread, in-order pipe).
-          if constexpr (KV_IN_TMEM) {
-            mbar_wait(BAR(KV_TMEM), 0);
+          // chain A: everything that does not depend on dS.
+          for (int n = 0;; ++n) {
+            const int idx = item_index(n);
+            if (idx < 0) break;
+            const Item it = load_item(idx);
+            const int NI = it.NI;
+            const uint32_t sK = buf_k(n), sV = buf_v(n);
+            // st = ring stage of the Q / dO tile (and of its sliver)
+            auto issue_S = [&](int st) {
+              const uint32_t q_smem = sQ + st * Cfg::kQ;
+              if constexpr (KV_IN_TMEM) issue_ST_ts(TM_S, TM_X, q_smem);
+              else issue_ST(TM_S, sK, q_smem);
+              if constexpr (AUG)      // S^T += ones * (c3/c1)^T : the exponent offset of every query column
+                umma_ss(tmem + TM_S, umma_desc_sw32(sOnes), umma_desc_sw32(sAug + st * 2 * Cfg::kSliver), idesc_s, 1u);
+            };
+            auto issue_dP = [&](int st) {
+              const uint32_t do_smem = sDO + st * Cfg::kQ;
+              if constexpr (KV_IN_TMEM) issue_ST_ts(TM_DP, TM_X + 32, do_smem);
+              else issue_ST(TM_DP, sV, do_smem);
+              if constexpr (AUG)      // dP^T += ones * (-delta)^T
+                umma_ss(tmem + TM_DP, umma_desc_sw32(sOnes),
+                        umma_desc_sw32(sAug + st * 2 * Cfg::kSliver + Cfg::kSliver), idesc_s, 1u);
+            };
+            const int st0 = tq % NST;
+            mbar_wait(BAR(KV_IN_TMEM ? K_TMEM : K_FULL), n & 1);
+            if (tq > 0) mbar_wait(BAR(S_FREE), (tq - 1) & 1);     // the previous item's last S^T is in registers
+            mbar_wait(BAR(Q_FULL + st0), (tq / NST) & 1);
             tc_fence_after();
-          }
-          mbar_wait(BAR(Q_FULL + 0), 0);
-          tc_fence_after();
-          issue_S(0);
-          umma_commit(BAR(S_FULL));
-          umma_commit(BAR(Q_EMPTY + 0));           // Q(0): this chain is done with it once S^T(0) completes
-          mbar_wait(BAR(DO_FULL + 0), 0);
-          tc_fence_after();
-          issue_dP(0);
-          umma_commit(BAR(DP_FULL));
-          umma_commit(BAR(DO_EMPTY + 0));
-          for (int i = 0; i < NI; ++i) {
-            const int st = i % NST, sn = (i + 1) % NST;
-            if (i + 1 < NI) {
-              mbar_wait(BAR(S_FREE), i & 1);
-              mbar_wait(BAR(Q_FULL + sn), ((i + 1) / NST) & 1);
+            issue_S(st0);
+            umma_commit(BAR(S_FULL));
+            umma_commit(BAR(Q_EMPTY + st0));         // Q: this chain is done with it once S^T completes
+            mbar_wait(BAR(KV_IN_TMEM ? V_TMEM : V_FULL), n & 1);
+            mbar_wait(BAR(DO_FULL + st0), (tq / NST) & 1);
+            tc_fence_after();
+            issue_dP(st0);                           // (behind the previous item's last dV: same thread, in-order pipe)
+            umma_commit(BAR(DP_FULL));
+            umma_commit(BAR(DO_EMPTY + st0));
+            for (int i = 0; i < NI; ++i) {
+              const int t = tq + i;
+              const int st = t % NST, sn = (t + 1) % NST;
+              if (i + 1 < NI) {
+                mbar_wait(BAR(S_FREE), t & 1);
+                mbar_wait(BAR(Q_FULL + sn), ((t + 1) / NST) & 1);
+                tc_fence_after();
+                issue_S(sn);
+                umma_commit(BAR(S_FULL));
+                umma_commit(BAR(Q_EMPTY + sn));
+                if (n == 0) FCSA_TR(0, i, 0);
+              }
+              mbar_wait(BAR(P_FULL), t & 1);
+              if (i == 0 && n > 0) mbar_wait(BAR(DV_FREE), (n - 1) & 1);   // the previous item's dV has been read out
               tc_fence_after();
-              issue_S(sn);
-              umma_commit(BAR(S_FULL));
-              umma_commit(BAR(Q_EMPTY + sn));
-              FCSA_TR(0, i, 0);
-            }
-            mbar_wait(BAR(P_FULL), i & 1);
-            tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < QT / 16; ++kk)
-              umma_ts(tmem + TM_DV, tmem + TM_DP + p_col(kk),
-                      umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(BAR(PV_DONE));
-            umma_commit(BAR(DO_EMPTY + st));       // dO(i): dV is done with it
-            FCSA_TR(0, i, 1);
-            if (i + 1 < NI) {
-              mbar_wait(BAR(DO_FULL + sn), ((i + 1) / NST) & 1);
-              tc_fence_after();
-              issue_dP(sn);
-              umma_commit(BAR(DP_FULL));
-              umma_commit(BAR(DO_EMPTY + sn));
-              FCSA_TR(0, i, 3);
+              for (int kk = 0; kk < QT / 16; ++kk)
+                umma_ts(tmem + TM_DV, tmem + TM_DP + p_col(kk),
+                        umma_desc_sw128(sDO + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
+                        (i > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(BAR(PV_DONE));
+              umma_commit(BAR(DO_EMPTY + st));       // dO(i): dV is done with it
+              if (n == 0) FCSA_TR(0, i, 1);
+              if (i + 1 < NI) {
+                mbar_wait(BAR(DO_FULL + sn), ((t + 1) / NST) & 1);
+                tc_fence_after();
+                issue_dP(sn);
+                umma_commit(BAR(DP_FULL));
+                umma_commit(BAR(DO_EMPTY + sn));
+                if (n == 0) FCSA_TR(0, i, 3);
+              }
             }
+            umma_commit(BAR(DKV_FULL));
+            tq += NI;
           }
-          umma_commit(BAR(DKV_FULL));
         } else {
           // chain B: the consumers of dS(i).  dK reads it from TMEM (the dQ accumulator columns),
           // then dQ(i) overwrites those columns - same issuing thread, in-order pipe.
-          for (int i = 0; i < NI; ++i) {
-            const int st = i % NST;
-            mbar_wait(BAR(DS_FULL), i & 1);
-            tc_fence_after();
+          for (int n = 0;; ++n) {
+            const int idx = item_index(n);
+            if (idx < 0) break;
+            const Item it = load_item(idx);
+            const int NI = it.NI;
+            const uint32_t sK = buf_k(n);
+            mbar_wait(BAR(KV_IN_TMEM ? K_TMEM : K_FULL), n & 1);   // dQ reads K from shared memory (K_TMEM: it has landed)
+            for (int i = 0; i < NI; ++i) {
+              const int t = tq + i;
+              const int st = t % NST;
+              mbar_wait(BAR(DS_FULL), t & 1);
+              if (i == 0 && n > 0) mbar_wait(BAR(DK_FREE), (n - 1) & 1);   // the previous item's dK has been read out
+              tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < QT / 16; ++kk)
-              umma_ts(tmem + TM_DK, tmem + TM_DQ + ds_col(kk),
-                      umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(BAR(Q_EMPTY + st));
-            FCSA_TR(0, i, 2);
+              for (int kk = 0; kk < QT / 16; ++kk)
+                umma_ts(tmem + TM_DK, tmem + TM_DQ + ds_col(kk),
+                        umma_desc_sw128(sQ + st * Cfg::kQ + kk * 2048, QCHUNK, 1024), idesc_ts,
+                        (i > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(BAR(Q_EMPTY + st));
+              if (n == 0) FCSA_TR(0, i, 2);
 #pragma unroll
 #ifdef FCSA_EXP_NO_DQMMA
-            if (false)
+              if (false)
 #endif
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint64_t d_ds = umma_desc_sw128(sDS + kk * 2048, 16384, 1024);
-              const uint64_t d_k = umma_desc_sw128(sK + kk * 2048, 16384, 1024);
-              if (D == 64) umma_ss(tmem + TM_DQ, d_ds, d_k, idesc_dq, kk > 0 ? 1u : 0u);
-              else umma_ss(tmem + TM_DQ, d_k, d_ds, idesc_dq, kk > 0 ? 1u : 0u);
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t d_ds = umma_desc_sw128(sDS + kk * 2048, 16384, 1024);
+                const uint64_t d_k = umma_desc_sw128(sK + kk * 2048, 16384, 1024);
+                if (D == 64) umma_ss(tmem + TM_DQ, d_ds, d_k, idesc_dq, kk > 0 ? 1u : 0u);
+                else umma_ss(tmem + TM_DQ, d_k, d_ds, idesc_dq, kk > 0 ? 1u : 0u);
+              }
+              umma_commit(BAR(DQ_FULL));
+              if (n == 0) FCSA_TR(0, i, 4);
             }
-            umma_commit(BAR(DQ_FULL));
-            FCSA_TR(0, i, 4);
+            umma_commit(BAR(KS_FREE));                // the MMAs are done with K's shared-memory buffer
+            umma_commit(BAR(DKV_FULL));
+            tq += NI;
           }
-          umma_commit(BAR(DKV_FULL));
         }
       }
     }
@@ -706,7 +759,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     reg_alloc<104>();   // 4 x 104 + 64 = 5 x 96: the pool is what the CTA was launched with (640 x 96)
     const int wq = warp & 3;
     const int r = wq * 32 + lane;            // key row inside the tile
-    const int key_g = key0 + r;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     constexpr int CW = QT / 4;               // query columns per warpgroup (32 or 16)
     const int cq0 = wg * CW;
@@ -728,50 +780,51 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // dQ of tile j: this warp's 32 rows x 16 accumulator columns -> registers.  The same (lanes,
     // columns) receive this thread's packed dS^T of the next tile, so no other thread is involved.
     uint32_t dqv[16];
-    auto load_dq = [&](int j) {
-      mbar_wait(BAR(DQ_FULL), j & 1);
-      if (tr_lane) FCSA_TR(3, j, 0);
+    // t = running index of the tile over all items (parity of its DQ_FULL phase)
+    auto load_dq = [&](int t) {
+      mbar_wait(BAR(DQ_FULL), t & 1);
+      if (tr_lane) FCSA_TR(3, t, 0);
       tc_fence_after();
       tmem_ld_x16(tDQ, dqv);
       tmem_ld_wait();
-#ifdef FCSA_EXP_RED_V4
-      {
-        // straight from registers: four 16-byte vector reductions per thread, 512 contiguous bytes per warp
-        float* dst = a.dq_acc + (((long long)bh * a.nqt + (i_lo + j)) * 4 + wq) * 2048 + wg * 512 + lane * 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          red_add_v4_f32(dst + c * 128, __uint_as_float(dqv[4 * c]), __uint_as_float(dqv[4 * c + 1]),
-                         __uint_as_float(dqv[4 * c + 2]), __uint_as_float(dqv[4 * c + 3]));
-      }
-#else
       // the previous bulk reduce must have finished reading the staging buffer
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         sts128(my_stage + c * 512 + lane * 16, dqv[4 * c], dqv[4 * c + 1], dqv[4 * c + 2], dqv[4 * c + 3]);
-#endif
     };
-    // after a fence.proxy.async: staged dQ of tile j -> global accumulator (TMA reduce-add, 2 KB)
-    auto reduce_dq = [&](int j) {
-#ifdef FCSA_EXP_RED_V4
-      return;
-#endif
+    // after a fence.proxy.async: the staged dQ tile -> global accumulator (TMA reduce-add, 2 KB per warp);
+    // dst = this warp's 2 KB of the tile's accumulator
+    auto reduce_dq = [&](float* dst) {
       __syncwarp();
 #ifndef FCSA_EXP_SKIP_REDUCE
       if (lane == 0) {
-        float* dst = a.dq_acc + (((long long)bh * a.nqt + (i_lo + j)) * 4 + wq) * 2048 + wg * 512;
         bulk_reduce_add_f32(dst, my_stage, 2048);
         bulk_commit_group();
       }
 #endif
-      if (tr_lane) FCSA_TR(3, j, 1);
     };
+    auto dq_dst = [&](int bh, int qt) -> float* {
+      return a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048 + wg * 512;
+    };
+    float* prev_dst = nullptr;               // accumulator tile of the previous query tile: drained one tile late
+    int tq = 0;                              // query tiles so far, over all items
+    const float c1 = a.c1;
+    for (int n = 0;; ++n) {
+    const int idx = item_index(n);
+    if (idx < 0) break;
+    const Item it = load_item(idx);
+    const int b = it.b, h = it.h, hk = it.hk, bh = it.bh, key0 = it.key0, i_lo = it.i_lo, NI = it.NI;
+    const int key_g = key0 + r;
+    const uint32_t sK = buf_k(n);
     if constexpr (KV_IN_TMEM) {
-      // K (warpgroup 0) and V (warpgroup 1) rows -> TMEM as A operands: 64 features = 32 packed columns
-      if (wg < 2 && NI > 0) {
-        mbar_wait(BAR(KV_FULL), 0);
-        const uint32_t src = wg == 0 ? sK : sV;
+      // K (warpgroup 2) and V (warpgroup 3) rows -> TMEM as A operands: 64 features = 32 packed columns.
+      // (Warpgroups 0 and 1 are the ones that come out of the previous item's epilogue.)  The previous item's
+      // last S^T / dP^T MMAs - the readers of these columns - completed before these warps saw its last tile.
+      if (wg >= 2) {
+        mbar_wait(BAR(wg == 2 ? K_FULL : V_FULL), n & 1);
+        const uint32_t src = wg == 2 ? sK : buf_v(n);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t kv[16];
@@ -781,21 +834,21 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             kv[4 * c] = __float_as_uint(v4.x); kv[4 * c + 1] = __float_as_uint(v4.y);
             kv[4 * c + 2] = __float_as_uint(v4.z); kv[4 * c + 3] = __float_as_uint(v4.w);
           }
-          tmem_st_x16(lane_base + TM_X + 32 * wg + 16 * hf, kv);
+          tmem_st_x16(lane_base + TM_X + 32 * (wg - 2) + 16 * hf, kv);
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(BAR(KV_TMEM));
+        mbar_arrive(BAR(wg == 2 ? K_TMEM : V_TMEM));
       }
     }
     {
-      const float c1 = a.c1;
       bool key_ok = key_g < a.Nk;
       if (a.has_mask && key_ok) key_ok = a.mask[(long long)b * a.mask_sb + key_g] != 0;
       const bool tile_key_ragged = (key0 + 127 >= a.Nk) || a.has_mask;
 
       for (int i = 0; i < NI; ++i) {
-        const int st = i % NST, qt = i_lo + i;
+        const int t = tq + i;                 // running tile index: ring stage and barrier parities
+        const int st = t % NST, qt = i_lo + i;
         const int row0 = qt * QT;
         const uint32_t c3a = sStats + st * 1024 + cq0 * 4;           // c3 of this warpgroup's queries
         const uint32_t dla = sStats + st * 1024 + (QT + cq0) * 4;    // -delta of the same
@@ -809,8 +862,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (!key_ok) lo = 1000;
         }
         if (tr_lane) FCSA_TR(1, i, 0);
-        mbar_wait(BAR(Q_FULL + st), (i / NST) & 1);    // c3 / delta of this tile are in smem
-        mbar_wait(BAR(S_FULL), i & 1);
+        mbar_wait(BAR(Q_FULL + st), (t / NST) & 1);    // c3 / delta of this tile are in smem
+        mbar_wait(BAR(S_FULL), t & 1);
         if (tr_lane) FCSA_TR(1, i, 1);
         if (i == 0) FCSA_CTA_T(tr_lane, 2);
         tc_fence_after();
@@ -885,7 +938,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             dlv[e] = dl.x; dlv[e + 1] = dl.y; dlv[e + 2] = dl.z; dlv[e + 3] = dl.w;
           }
         }
-        mbar_wait(BAR(DP_FULL), i & 1);
+        mbar_wait(BAR(DP_FULL), t & 1);
         if (tr_lane) FCSA_TR(2, i, 0);
         tc_fence_after();
         uint32_t (&d)[CW] = s;                // the S^T registers are dead: reuse them for dP^T
@@ -917,7 +970,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         // ---- dQ(i-1) out of its accumulator columns (its MMA sits right behind dK(i-1): long done;
         // it has also released the shared-memory dS^T), then dS^T(i) into them
-        if (i > 0) load_dq(i - 1);
+        if (prev_dst != nullptr) load_dq(t - 1);
         if (tr_lane) FCSA_TR(2, i, 2);
         st_cw(tDS, ds);
         // the same CW queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
@@ -934,23 +987,17 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr_lane) FCSA_TR(2, i, 3);
         if (i == 0) FCSA_CTA_T(tr_lane, 3);
         if (i == NI - 1) FCSA_CTA_T(tr_lane, 4);
-        if (i > 0) reduce_dq(i - 1);
+        if (prev_dst != nullptr) reduce_dq(prev_dst);
+        prev_dst = dq_dst(bh, qt);
       }
-      if (NI > 0) {
-        load_dq(NI - 1);
-        fence_proxy_async_smem();
-        reduce_dq(NI - 1);
-      }
-      if (lane == 0) bulk_wait_group<0>();
-      __syncwarp();
-      FCSA_CTA_T(tr_lane, 5);
+      tq += NI;
     }
 
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
     if (wg < 2) {
     const int w = wg;
     if (NI > 0) {
-      mbar_wait(BAR(DKV_FULL), 0);
+      mbar_wait(BAR(DKV_FULL), n & 1);
       tc_fence_after();
     }
     const bool store_ok = key_g < a.Nk;
@@ -1002,6 +1049,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int x = 0; x < 32; ++x) acc[x] = 0;
       }
+      if (c == D / 32 - 1) {                   // the accumulator is in registers: the next item may overwrite it
+        tc_fence_before();
+        mbar_arrive(BAR(w == 0 ? DV_FREE : DK_FREE));
+      }
       if (fuse_l2) {
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
@@ -1051,7 +1102,17 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+    if (w == 1) mbar_arrive(BAR(KS_FREE));     // this thread's reads of K's shared-memory buffer are done
     }
+    }   // items
+    // the last query tile of the last item: its dQ tile is still in the accumulator columns
+    if (prev_dst != nullptr) {
+      load_dq(tq - 1);
+      fence_proxy_async_smem();
+      reduce_dq(prev_dst);
+    }
+    if (lane == 0) bulk_wait_group<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -1334,7 +1395,13 @@ int run_backward_t(const BwdHostArgs& h, cudaStream_t stream, int* launches, con
     auto kern = fcsa_bwd_kernel<T, D, BIAS>;
     e = ensure_dynamic_smem<fcsa_bwd_kernel<T, D, BIAS>>(Cfg::kSmem);
     if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(bwd)"; *ce = e; return FCSA_ERR_CUDA; }
-    const long long grid = (long long)((h.Nk + 127) / 128) * h.B * h.H;
+    // D = 64: persistent CTAs, one per SM, each walking its share of the (key tile, batch, head) items;
+    // D = 128 (K and V stay in shared memory for the whole item): one CTA per item.
+    // FCSA_BWD_GRID (tuning / A-B knob): number of CTAs; 0 = one CTA per item
+    const long long items = (long long)((h.Nk + 127) / 128) * h.B * h.H;
+    static const long long grid_env = [] { const char* ev = getenv("FCSA_BWD_GRID"); return ev ? atoll(ev) : -1LL; }();
+    long long grid = items;
+    if (D == 64 && grid_env != 0) grid = std::min<long long>(items, grid_env > 0 ? grid_env : device_sm_count());
     if (h.ev_start) cudaEventRecord(h.ev_start, stream);
     e = launch_pdl(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tq, tk, tv, tdo, taug, tones, a);
     if (h.ev_stop) cudaEventRecord(h.ev_stop, stream);

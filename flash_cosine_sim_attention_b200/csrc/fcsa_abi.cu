@@ -24,20 +24,7 @@
 
 namespace {
 
-// SM count of the CURRENT device (persistent helper kernels size their grid from it); cached per
-// device, thread-safe (relaxed atomics: a race only repeats the query)
-int sm_count() {
-  static std::atomic<int> cache[256];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const bool cacheable = dev >= 0 && dev < 256;
-  int n = cacheable ? cache[dev].load(std::memory_order_relaxed) : 0;
-  if (n == 0) {
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    if (cacheable) cache[dev].store(n, std::memory_order_relaxed);
-  }
-  return n;
-}
+int sm_count() { return fcsa::device_sm_count(); }
 
 thread_local char g_err[512] = "";
 cudaEvent_t g_ev[5][2] = {};   // 0 forward, 1 backward, 2 l2norm(q,k), 3 backward preprocess, 4 dq finish

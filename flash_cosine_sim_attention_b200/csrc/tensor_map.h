@@ -136,4 +136,19 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// SM count of the CURRENT device (persistent kernels size their grid from it); cached per device,
+// thread-safe (relaxed atomics: a race only repeats the query)
+inline int device_sm_count() {
+  static std::atomic<int> cache[256];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool cacheable = dev >= 0 && dev < 256;
+  int n = cacheable ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cacheable) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 }  // namespace fcsa
