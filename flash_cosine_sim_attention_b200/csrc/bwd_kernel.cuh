@@ -445,7 +445,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = warp >> 2;
-  FCSA_CTA_T(threadIdx.x == 0, 0);
   pdl_launch_dependents();
 
   // ---- work items -------------------------------------------------------------------------
@@ -522,7 +521,6 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();          // slivers / stats come from the preprocess kernel; accumulators are zero on entry
-  FCSA_CTA_T(threadIdx.x == 0, 1);
 
   if (wg == 4) {
     reg_dealloc<64>();
@@ -796,27 +794,31 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     };
     // after a fence.proxy.async: the staged dQ tile -> global accumulator (TMA reduce-add, 2 KB per warp);
     // dst = this warp's 2 KB of the tile's accumulator
-    auto reduce_dq = [&](float* dst) {
+    // tile = index of the query tile's accumulator in the workspace (bh * nqt + qt)
+    auto reduce_dq = [&](int tile) {
       __syncwarp();
 #ifndef FCSA_EXP_SKIP_REDUCE
       if (lane == 0) {
-        bulk_reduce_add_f32(dst, my_stage, 2048);
+        bulk_reduce_add_f32(a.dq_acc + ((long long)tile * 4 + wq) * 2048 + wg * 512, my_stage, 2048);
         bulk_commit_group();
       }
 #endif
     };
-    auto dq_dst = [&](int bh, int qt) -> float* {
-      return a.dq_acc + (((long long)bh * a.nqt + qt) * 4 + wq) * 2048 + wg * 512;
-    };
-    float* prev_dst = nullptr;               // accumulator tile of the previous query tile: drained one tile late
+    int prev_tile = -1;                      // accumulator tile of the previous query tile: drained one tile late
     int tq = 0;                              // query tiles so far, over all items
     const float c1 = a.c1;
     for (int n = 0;; ++n) {
-    const int idx = item_index(n);
+    // (broadcast from lane 0: tells the compiler that everything derived from the item is warp-uniform, so the
+    //  barrier waits of the tile loop stay on the uniform datapath, without reconvergence points)
+    const int idx = __shfl_sync(0xFFFFFFFFu, item_index(n), 0);
     if (idx < 0) break;
     const Item it = load_item(idx);
-    const int b = it.b, h = it.h, hk = it.hk, bh = it.bh, key0 = it.key0, i_lo = it.i_lo, NI = it.NI;
+    // (only what the tile loop needs stays live across it; the epilogue re-derives batch / head from idx)
+    const int key0 = it.key0, i_lo = it.i_lo, NI = it.NI;
+    const int tile0 = it.bh * a.nqt;         // accumulator tile index of query tile 0 of this (batch, head)
+    [[maybe_unused]] const int b = it.b, h = it.h;   // tile loop: bias instantiation only
     const int key_g = key0 + r;
+    FCSA_ITEM_T(tr_lane, idx, 0);
     const uint32_t sK = buf_k(n);
     if constexpr (KV_IN_TMEM) {
       // K (warpgroup 2) and V (warpgroup 3) rows -> TMEM as A operands: 64 features = 32 packed columns.
@@ -843,11 +845,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     {
       bool key_ok = key_g < a.Nk;
-      if (a.has_mask && key_ok) key_ok = a.mask[(long long)b * a.mask_sb + key_g] != 0;
+      if (a.has_mask && key_ok) key_ok = a.mask[(long long)it.b * a.mask_sb + key_g] != 0;
       const bool tile_key_ragged = (key0 + 127 >= a.Nk) || a.has_mask;
 
       for (int i = 0; i < NI; ++i) {
-        const int t = tq + i;                 // running tile index: ring stage and barrier parities
+        // running tile index: ring stage and barrier parities (the broadcast keeps it, and every wait below,
+        // on the uniform datapath - a loop-carried sum over items is not recognised as warp-uniform)
+        const int t = __shfl_sync(0xFFFFFFFFu, tq + i, 0);
         const int st = t % NST, qt = i_lo + i;
         const int row0 = qt * QT;
         const uint32_t c3a = sStats + st * 1024 + cq0 * 4;           // c3 of this warpgroup's queries
@@ -865,7 +869,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(BAR(Q_FULL + st), (t / NST) & 1);    // c3 / delta of this tile are in smem
         mbar_wait(BAR(S_FULL), t & 1);
         if (tr_lane) FCSA_TR(1, i, 1);
-        if (i == 0) FCSA_CTA_T(tr_lane, 2);
+        if (i == 0) FCSA_ITEM_T(tr_lane, idx, 2);
         tc_fence_after();
         // ---- exp stage.  The shared-memory operands are fetched in one batch so the exp chain
         // (FFMA -> MUFU -> pack) of CW independent elements can be pipelined freely.  The masked
@@ -970,7 +974,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         // ---- dQ(i-1) out of its accumulator columns (its MMA sits right behind dK(i-1): long done;
         // it has also released the shared-memory dS^T), then dS^T(i) into them
-        if (prev_dst != nullptr) load_dq(t - 1);
+        if (prev_tile >= 0) load_dq(t - 1);
         if (tr_lane) FCSA_TR(2, i, 2);
         st_cw(tDS, ds);
         // the same CW queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
@@ -985,10 +989,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         mbar_arrive(BAR(DS_FULL));
         if (tr_lane) FCSA_TR(2, i, 3);
-        if (i == 0) FCSA_CTA_T(tr_lane, 3);
-        if (i == NI - 1) FCSA_CTA_T(tr_lane, 4);
-        if (prev_dst != nullptr) reduce_dq(prev_dst);
-        prev_dst = dq_dst(bh, qt);
+        if (i == 0) FCSA_ITEM_T(tr_lane, idx, 3);
+        if (i == NI - 1) FCSA_ITEM_T(tr_lane, idx, 4);
+        if (prev_tile >= 0) reduce_dq(prev_tile);
+        prev_tile = tile0 + qt;
       }
       tq += NI;
     }
@@ -996,6 +1000,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK * scale -------------------
     if (wg < 2) {
     const int w = wg;
+    int idx_e = idx;
+    asm volatile("" : "+r"(idx_e));            // opaque copy: batch / head are recomputed here, not kept in registers
+    const Item ie = load_item(idx_e);
+    const int b = ie.b, h = ie.h, hk = ie.hk;
     if (NI > 0) {
       mbar_wait(BAR(DKV_FULL), n & 1);
       tc_fence_after();
@@ -1103,23 +1111,22 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     if (w == 1) mbar_arrive(BAR(KS_FREE));     // this thread's reads of K's shared-memory buffer are done
+    FCSA_ITEM_T(tr_lane, idx, 6);
     }
     }   // items
     // the last query tile of the last item: its dQ tile is still in the accumulator columns
-    if (prev_dst != nullptr) {
+    if (prev_tile >= 0) {
       load_dq(tq - 1);
       fence_proxy_async_smem();
-      reduce_dq(prev_dst);
+      reduce_dq(prev_tile);
     }
     if (lane == 0) bulk_wait_group<0>();
     __syncwarp();
   }
 
   tc_fence_before();
-  FCSA_CTA_T(threadIdx.x == 0, 6);
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem, 512);
-  FCSA_CTA_T(threadIdx.x == 32 * 17, 7);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -47,8 +47,21 @@ __device__ long long g_fcsa_cta_t[4096][10];
       }                                                                               \
     }                                                                                 \
   } while (0)
+// the same, one row per work item of a persistent kernel
+#define FCSA_ITEM_T(cond, item, slot)                                                 \
+  do {                                                                                \
+    if ((cond) && (item) < 4096) {                                                    \
+      g_fcsa_cta_t[item][slot] = clock64();                                           \
+      if ((slot) == 0) {                                                              \
+        unsigned smid_;                                                               \
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                            \
+        g_fcsa_cta_t[item][8] = smid_;                                                \
+      }                                                                               \
+    }                                                                                 \
+  } while (0)
 #else
 #define FCSA_CTA_T(cond, slot) do { } while (0)
+#define FCSA_ITEM_T(cond, item, slot) do { } while (0)
 #endif
 
 namespace fcsa {

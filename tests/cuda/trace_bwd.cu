@@ -77,29 +77,32 @@ int main(int argc, char** argv) {
   printf("B %d H %d Nq %d Nk %d causal %d: main kernel best of %d: %.1f us\n", B, H, Nq, Nk, causal, reps, best * 1e3);
 #ifdef FCSA_CTA_TIMELINE
   {
-    const int nblk = ((Nk + 127) / 128) * B * H;
+    // one row per work item (key tile x batch x head); per SM: the items it ran, in start order
+    const int nitems = ((Nk + 127) / 128) * B * H;
     static long long ct[4096][10];
     CK(cudaMemcpyFromSymbol(ct, g_fcsa_cta_t, sizeof(ct)));
-    printf("slots: 0 entry, 1 setup done, 2 first S seen, 3 first dS handed over, 4 last dS handed over, 5 dQ drained, 6 dK/dV stored, 7 exit\n");
-    double gap = 0, sl[8] = {0}; int n = 0, ngap = 0; double ni_sum = 0;
+    printf("per item: start(after previous item's last dS) | start->first S seen, ->first dS handed over, ->last dS handed over, ->dK/dV stored; tiles\n");
+    double s_first = 0, s_ds = 0, s_body = 0, s_epi = 0, s_gap = 0; int n = 0, ngap = 0; double tiles = 0;
     for (int sm = 0; sm < 148; ++sm) {
       std::vector<int> ids;
-      for (int i = 0; i < nblk && i < 4096; ++i) if (ct[i][8] == sm) ids.push_back(i);
+      for (int i = 0; i < nitems && i < 4096; ++i) if (ct[i][8] == sm && ct[i][0]) ids.push_back(i);
       std::sort(ids.begin(), ids.end(), [&](int x, int y) { return ct[x][0] < ct[y][0]; });
       for (size_t k2 = 0; k2 < ids.size(); ++k2) {
         const int id = ids[k2];
-        if (k2 > 0) { gap += ct[id][0] - ct[ids[k2 - 1]][7]; ++ngap; }
-        for (int s2 = 1; s2 < 8; ++s2) sl[s2] += ct[id][s2] - ct[id][s2 - 1];
-        ++n;
-        if (sm < 2) {
-          printf("sm %d cta %4d (key tile %2d): gap %6lld |", sm, id, id / (B * H), k2 ? ct[id][0] - ct[ids[k2 - 1]][7] : 0LL);
-          for (int s2 = 0; s2 < 8; ++s2) printf(" %7lld", ct[id][s2] - ct[id][0]);
-          printf("\n");
-        }
+        const int jt = id / (B * H);
+        int ni = (Nq + 127) / 128;
+        if (causal) { int x = jt * 128 - (Nk - Nq) - 127; int ilo = x <= 0 ? 0 : (x + 127) / 128; ni -= ilo; }
+        const long long gap = k2 ? ct[id][0] - ct[ids[k2 - 1]][4] : 0;
+        if (k2) { s_gap += gap; ++ngap; }
+        s_first += ct[id][2] - ct[id][0]; s_ds += ct[id][3] - ct[id][2]; s_body += ct[id][4] - ct[id][3]; s_epi += ct[id][6] - ct[id][4];
+        tiles += ni - 1; ++n;
+        if (sm < 2)
+          printf("sm %d item %4d (key tile %2d, %2d tiles): after prev last dS %6lld | %6lld %6lld %7lld %6lld\n", sm, id, jt, ni, gap,
+                 ct[id][2] - ct[id][0], ct[id][3] - ct[id][2], ct[id][4] - ct[id][3], ct[id][6] - ct[id][4]);
       }
     }
-    printf("mean per CTA (cycles): launch gap %.0f | entry->setup %.0f, ->first S %.0f, ->first dS %.0f, ->last dS %.0f, ->dQ drained %.0f, ->dK/dV stored %.0f, ->exit %.0f  (%d CTAs)\n",
-           gap / (ngap ? ngap : 1), sl[1] / n, sl[2] / n, sl[3] / n, sl[4] / n, sl[5] / n, sl[6] / n, sl[7] / n, n);
+    printf("means (cycles): prev last dS -> item start %.0f | start -> first S %.0f, -> first dS %.0f, first -> last dS %.0f (%.0f per tile), last dS -> dK/dV stored %.0f  (%d items)\n",
+           s_gap / (ngap ? ngap : 1), s_first / n, s_ds / n, s_body / n, s_body / tiles, s_epi / n, n);
   }
 #endif
 #ifdef FCSA_TRACE
