@@ -1009,6 +1009,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
     }
     const bool store_ok = key_g < a.Nk;
+    // the stores below go through this warp's dQ staging buffer: its last bulk reduce must have read it
+    if (lane == 0) bulk_wait_group_read<0>();
+    __syncwarp();
     const uint32_t tACC = lane_base + (w == 0 ? TM_DV : TM_DK);
     const float mul = (w == 0) ? 1.0f : a.scale;
     const bool shared_kv = (a.kv_heads == 1 && a.H > 1);
@@ -1079,35 +1082,34 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
-      if (store_ok && a.out_f32 && !shared_kv) {
-        float* base = (w == 0)
-            ? reinterpret_cast<float*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + (long long)key_g * a.dv_sn
-            : reinterpret_cast<float*>(a.dk) + b * a.dk_sb + hk * a.dk_sh + (long long)key_g * a.dk_sn;
+      if (!shared_kv) {
+        // this warp's 32 key rows x 32 features, through its 2 KB dQ staging buffer (coalesced: see warp_store_rows64)
+        const int valid = min(32, max(0, a.Nk - (key0 + wq * 32)));
+        const long long row_off = (long long)(key0 + wq * 32);
+        uint32_t w16[16];
+        if (a.out_f32) {
+          float* base = ((w == 0) ? reinterpret_cast<float*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + row_off * a.dv_sn
+                                  : reinterpret_cast<float*>(a.dk) + b * a.dk_sb + hk * a.dk_sh + row_off * a.dk_sn) + c * 32;
 #pragma unroll
-        for (int v4 = 0; v4 < 8; ++v4)
-          *reinterpret_cast<float4*>(base + c * 32 + v4 * 4) =
-              make_float4(__uint_as_float(acc[4 * v4 + 0]) * mul, __uint_as_float(acc[4 * v4 + 1]) * mul,
-                          __uint_as_float(acc[4 * v4 + 2]) * mul, __uint_as_float(acc[4 * v4 + 3]) * mul);
-      } else if (store_ok) {
-        if (!shared_kv) {
-          T* base = (w == 0)
-              ? reinterpret_cast<T*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + (long long)key_g * a.dv_sn
-              : reinterpret_cast<T*>(a.dk) + b * a.dk_sb + hk * a.dk_sh + (long long)key_g * a.dk_sn;
+          for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 o4;
-            o4.x = pack2<T>(__uint_as_float(acc[8 * v4 + 0]) * mul, __uint_as_float(acc[8 * v4 + 1]) * mul);
-            o4.y = pack2<T>(__uint_as_float(acc[8 * v4 + 2]) * mul, __uint_as_float(acc[8 * v4 + 3]) * mul);
-            o4.z = pack2<T>(__uint_as_float(acc[8 * v4 + 4]) * mul, __uint_as_float(acc[8 * v4 + 5]) * mul);
-            o4.w = pack2<T>(__uint_as_float(acc[8 * v4 + 6]) * mul, __uint_as_float(acc[8 * v4 + 7]) * mul);
-            *reinterpret_cast<uint4*>(base + c * 32 + v4 * 8) = o4;
+            for (int x = 0; x < 16; ++x) w16[x] = __float_as_uint(__uint_as_float(acc[16 * hf + x]) * mul);
+            warp_store_rows64(my_stage, lane, w16, reinterpret_cast<uint8_t*>(base + 16 * hf),
+                              ((w == 0) ? a.dv_sn : a.dk_sn) * 4, valid);
           }
         } else {
-          // keys/values shared by all heads: sum over heads in fp32 (reference: cu:1613-1619)
-          float* accp = ((w == 0) ? a.dv_acc : a.dk_acc) + ((long long)b * a.Nk + key_g) * D + c * 32;
+          T* base = ((w == 0) ? reinterpret_cast<T*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + row_off * a.dv_sn
+                              : reinterpret_cast<T*>(a.dk) + b * a.dk_sb + hk * a.dk_sh + row_off * a.dk_sn) + c * 32;
 #pragma unroll
-          for (int x = 0; x < 32; ++x) atomicAdd(accp + x, __uint_as_float(acc[x]) * mul);
+          for (int x = 0; x < 16; ++x)
+            w16[x] = pack2<T>(__uint_as_float(acc[2 * x]) * mul, __uint_as_float(acc[2 * x + 1]) * mul);
+          warp_store_rows64(my_stage, lane, w16, reinterpret_cast<uint8_t*>(base), ((w == 0) ? a.dv_sn : a.dk_sn) * 2, valid);
         }
+      } else if (store_ok) {
+        // keys/values shared by all heads: sum over heads in fp32 (reference: cu:1613-1619)
+        float* accp = ((w == 0) ? a.dv_acc : a.dk_acc) + ((long long)b * a.Nk + key_g) * D + c * 32;
+#pragma unroll
+        for (int x = 0; x < 32; ++x) atomicAdd(accp + x, __uint_as_float(acc[x]) * mul);
       }
     }
     if (w == 1) mbar_arrive(BAR(KS_FREE));     // this thread's reads of K's shared-memory buffer are done

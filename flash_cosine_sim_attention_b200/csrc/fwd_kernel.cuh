@@ -28,12 +28,6 @@
 
 #include "sm100_primitives.cuh"
 
-#ifndef FCSA_FWD_SWAP
-// 1: the two tile engines of a CTA swap the upper / lower 128 rows from item to item.  Causal: the upper rows
-// see one key tile fewer, so a fixed assignment lets one engine run ahead by one iteration per item until the
-// shared K/V ring stops it; alternating keeps the two within one iteration of each other.
-#define FCSA_FWD_SWAP 1
-#endif
 #ifndef FCSA_POLY_EVERY
 #define FCSA_POLY_EVERY 4   // forward, D = 64: 1 of every N exp pairs runs on the FMA pipe (0 = none)
 #endif
@@ -71,7 +65,10 @@ struct FwdCfg {
   static constexpr int kOffK = 2 * kTile;
   static constexpr int kOffV = kOffK + kKS * kTile;
   static constexpr int kOffL = kOffV + kVS * kTile;   // partial row sums: 2 tiles x 2 halves x 128 floats
-  static constexpr int kOffBar = kOffL + 4096;        // (double-buffered over work items)
+  // D = 64: 2 KB per softmax warp to turn the epilogue's row-per-lane stores into coalesced ones
+  static constexpr bool kStageO = (D == 64);
+  static constexpr int kOffStage = kOffL + 4096;      // (the row sums are double-buffered over work items)
+  static constexpr int kOffBar = kOffStage + (kStageO ? 16 * 2048 : 0);
   static constexpr int kSmem = kOffBar + 256 + 1024;  // + alignment slack
   static constexpr int kThreads = 640;                // 16 softmax warps + 4 service warps
 };
@@ -207,8 +204,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_expect_tx(BAR(Q_FULL + t), TILE);
 #pragma unroll
           for (int ch = 0; ch < DCH; ++ch)
-            tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL + t), ch * 64, it.m0 + 128 * (t ^ (k & FCSA_FWD_SWAP)),
-                        it.h, it.b);
+            tma_load_4d(sQ + t * TILE + ch * 16384, &tm_q, BAR(Q_FULL + t), ch * 64, it.m0 + 128 * t, it.h, it.b);
         }
         for (int j = 0; j < it.NT; ++j, ++g) {
           const int ks = g % KS, vs = g % VS;
@@ -241,7 +237,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int idx = item_index(k);
         if (idx < 0) break;
         const Item it = load_item(idx);
-        const int nt = (t ^ (k & FCSA_FWD_SWAP)) ? it.n_t[1] : it.n_t[0], NT = it.NT;
+        const int nt = t ? it.n_t[1] : it.n_t[0], NT = it.NT;
         // gj = ring position of key tile j of this item; `last`: no further S_t in this item -> Q_t may be replaced
         auto issue_S = [&](int gj, bool last) {
           const int ks = gj % KS;
@@ -272,8 +268,14 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         } else {
           // nothing to compute for this tile: keep its per-item phases moving, in step with the producer
           // (an issuer running two items ahead would alias the parity the producer waits for)
+          // O_FULL: only once the softmax warps are through with the previous item (O_FREE).  Without that an
+          // issuer running through a series of empty items flips O_FULL faster than the softmax warps look at
+          // it (parity aliasing), and a plain arrive could overtake the previous item's tcgen05.commit, which
+          // is still in flight.  (Q_EMPTY needs no such care: Q_FULL(k) is only loaded after the previous
+          // item's Q_EMPTY phase, so producer and issuer pace each other.)
           mbar_wait(BAR(Q_FULL + t), k & 1);
           mbar_arrive(BAR(Q_EMPTY + t));
+          if (k > 0) mbar_wait(BAR(O_FREE + t), (k - 1) & 1);
           mbar_arrive(BAR(O_FULL + t));
         }
         for (int j = 0; j < NT; ++j) {
@@ -339,7 +341,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int idx = item_index(k);
     if (idx < 0) break;
     const Item it = load_item(idx);
-    const int tl = t ^ (k & FCSA_FWD_SWAP);  // which 128 rows of the item this tile engine takes (see FCSA_FWD_SWAP)
+    const int tl = t;                        // which 128 rows of the item this tile engine takes
     const int b = it.b, h = it.h, m0 = it.m0, nt = tl ? it.n_t[1] : it.n_t[0];
     const int row_g = m0 + 128 * tl + r;     // global query row
     // bias row of this query (clamped for the padding rows of the last tile, which are never stored)
@@ -497,7 +499,28 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tc_fence_before();
           mbar_arrive(BAR(O_FREE + t));
         }
-        if (row_ok && o_f32) {
+        if constexpr (Cfg::kStageO) {
+          // this warp's 32 query rows x 32 features through its 2 KB staging buffer (see warp_store_rows64)
+          const uint32_t stage = smem_u32(smem + Cfg::kOffStage) + warp * 2048;
+          const int row_w = m0 + 128 * tl + wq * 32;                // first query row of this warp
+          const int valid = min(32, max(0, a.Nq - row_w));
+          const long long w_off = (long long)b * a.o_sb + (long long)h * a.o_sh + (long long)row_w * a.o_sn + c * 32;
+          uint32_t w16[16];
+          if (o_f32) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+              for (int x = 0; x < 16; ++x) w16[x] = __float_as_uint(__uint_as_float(acc[16 * hf + x]) * inv);
+              warp_store_rows64(stage, lane, w16, reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(a.o) + w_off + 16 * hf),
+                                a.o_sn * 4, valid);
+            }
+          } else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x)
+              w16[x] = pack2<T>(__uint_as_float(acc[2 * x]) * inv, __uint_as_float(acc[2 * x + 1]) * inv);
+            warp_store_rows64(stage, lane, w16, reinterpret_cast<uint8_t*>(reinterpret_cast<T*>(a.o) + w_off), a.o_sn * 2, valid);
+          }
+        } else if (row_ok && o_f32) {
 #pragma unroll
           for (int v = 0; v < 8; ++v)
             *reinterpret_cast<float4*>(orow32 + c * 32 + v * 4) =

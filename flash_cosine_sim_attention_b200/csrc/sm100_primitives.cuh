@@ -166,6 +166,27 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
+// One warp stores 32 rows x 64 bytes to global memory, row r at dst + r * row_stride_bytes, where lane r holds
+// row r in registers (w[16]).  Stored directly, each instruction would touch 32 different 128-byte lines with
+// 16 bytes each - the LSU serialises that into 32 wavefronts.  Going through 2 KB of shared memory (16-byte
+// chunks XOR-swizzled so that neither side has bank conflicts) every store instruction covers 8 rows x 64
+// contiguous bytes.  Rows >= valid_rows are not stored.  The caller owns `stage` (this warp only).
+__device__ __forceinline__ void warp_store_rows64(uint32_t stage, int lane, const uint32_t (&w)[16], uint8_t* dst,
+                                                  long long row_stride_bytes, int valid_rows) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    sts128(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = 8 * k + (lane >> 2);
+    const float4 v = lds128f(stage + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
+    if (row < valid_rows) *reinterpret_cast<float4*>(dst + row * row_stride_bytes + c * 16) = v;
+  }
+  __syncwarp();      // every lane has read its chunks: the stage may be rewritten
+}
+
 // Programmatic dependent launch: every kernel of a step is launched with the
 // programmatic-stream-serialization attribute.  `pdl_launch_dependents` (first thing in a kernel)
 // lets the next kernel of the stream start being scheduled as soon as all CTAs of this one have

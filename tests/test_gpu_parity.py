@@ -372,6 +372,33 @@ def test_many_batch_heads_merged(fcsa):
     assert torch.isfinite(qd.grad).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 300, 520, 260), (1, 1500, 300, 300), (3, 200, 16, 1024), (1, 700, 700, 300)])
+def test_persistent_ctas_many_short_work_items(fcsa, shape):
+    """Persistent kernels: several hundred short work items per CTA, including query blocks with no visible key
+    (causal, more queries than keys: items without any key tile) and half-empty query blocks - the cases where
+    an item-level hand-shake can alias its parity or be overtaken."""
+    dt = torch.bfloat16
+    B, H, Nq, Nk = shape
+    g = torch.Generator().manual_seed(41)
+    q, do = (torch.randn(B, H, Nq, 64, generator=g).to(dt) for _ in range(2))
+    k, v = (torch.randn(B, H, Nk, 64, generator=g).to(dt) for _ in range(2))
+    qd, kd, vd = (t.cuda().requires_grad_() for t in (q, k, v))
+    for _ in range(2):                                 # twice: the zeroed workspace must come back clean
+        for t in (qd, kd, vd):
+            t.grad = None
+        o = fcsa.flash_cosine_sim_attention(qd, kd, vd, causal=True)
+        o.backward(do.cuda())
+        torch.cuda.synchronize()
+    for hh in (0, H // 2, H - 1):
+        sl = (slice(B - 1, B), slice(hh, hh + 1))
+        ref = oracle.attention(q[sl].float().numpy(), k[sl].float().numpy(), v[sl].float().numpy(), causal=True,
+                               d_out=do[sl].float().numpy(), round_qk="bf16", empty_rows="zero")
+        assert rel_err(o[sl], ref[0]) <= TOL_OUT[dt]
+        for t, r in zip((qd, kd, vd), ref[1:]):
+            assert rel_err(t.grad[sl], r) <= TOL_GRAD[dt]
+    assert torch.isfinite(qd.grad).all() and torch.isfinite(kd.grad).all()
+
+
 def test_two_streams_have_their_own_workspaces(fcsa):
     """Backward calls on two streams must not share the persistent accumulator."""
     dt = torch.bfloat16
