@@ -1009,9 +1009,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
     }
     const bool store_ok = key_g < a.Nk;
-    // the stores below go through this warp's dQ staging buffer: its last bulk reduce must have read it
-    if (lane == 0) bulk_wait_group_read<0>();
-    __syncwarp();
+    // The stores below are staged through the chunks of the dS^T tile that THIS warp writes in the main loop
+    // (32 key rows x its warpgroup's 64 bytes of query columns): the last dQ MMA - the tile's only reader -
+    // completed before DKV_FULL, and the next writer is this warp itself.
+    // (D = 128, one item per CTA, 64-query tiles: a warp's own chunks are only 32 bytes wide - warpgroups 0 / 1
+    //  take chunk columns 0-3 / 4-7 of their key rows; the other warps wrote them last before the final dS hand-over)
+    const uint32_t st_tile = sDS + (D == 64 ? (cq0 >> 6) * 16384 : 0);
+    const int st_c0 = (D == 64) ? ((cq0 & 63) >> 3) : 4 * wg;
     const uint32_t tACC = lane_base + (w == 0 ? TM_DV : TM_DK);
     const float mul = (w == 0) ? 1.0f : a.scale;
     const bool shared_kv = (a.kv_heads == 1 && a.H > 1);
@@ -1083,7 +1087,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       if (!shared_kv) {
-        // this warp's 32 key rows x 32 features, through its 2 KB dQ staging buffer (coalesced: see warp_store_rows64)
+        // this warp's 32 key rows x 32 features, coalesced through shared memory (see warp_store_rows64)
         const int valid = min(32, max(0, a.Nk - (key0 + wq * 32)));
         const long long row_off = (long long)(key0 + wq * 32);
         uint32_t w16[16];
@@ -1094,8 +1098,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
             for (int x = 0; x < 16; ++x) w16[x] = __float_as_uint(__uint_as_float(acc[16 * hf + x]) * mul);
-            warp_store_rows64(my_stage, lane, w16, reinterpret_cast<uint8_t*>(base + 16 * hf),
-                              ((w == 0) ? a.dv_sn : a.dk_sn) * 4, valid);
+            warp_store_rows64_sw128(st_tile, wq * 32, st_c0, lane, w16, reinterpret_cast<uint8_t*>(base + 16 * hf),
+                                    ((w == 0) ? a.dv_sn : a.dk_sn) * 4, valid);
           }
         } else {
           T* base = ((w == 0) ? reinterpret_cast<T*>(a.dv) + b * a.dv_sb + hk * a.dv_sh + row_off * a.dv_sn
@@ -1103,7 +1107,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int x = 0; x < 16; ++x)
             w16[x] = pack2<T>(__uint_as_float(acc[2 * x]) * mul, __uint_as_float(acc[2 * x + 1]) * mul);
-          warp_store_rows64(my_stage, lane, w16, reinterpret_cast<uint8_t*>(base), ((w == 0) ? a.dv_sn : a.dk_sn) * 2, valid);
+          warp_store_rows64_sw128(st_tile, wq * 32, st_c0, lane, w16, reinterpret_cast<uint8_t*>(base),
+                                  ((w == 0) ? a.dv_sn : a.dk_sn) * 2, valid);
         }
       } else if (store_ok) {
         // keys/values shared by all heads: sum over heads in fp32 (reference: cu:1613-1619)

@@ -522,4 +522,24 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);
 }
 
+// warp_store_rows64 with the staging chunks laid out like 4 consecutive 16-byte columns (c0 .. c0+3, c0 a multiple
+// of 4) of a 128-byte-swizzled tile at `tile`: 32 rows r0 .. r0+31.  The backward uses it with the chunks of its
+// dS^T staging tile that this very warp writes during the main loop, so the epilogue needs no buffer of its own
+// and no other warp is involved.
+__device__ __forceinline__ void warp_store_rows64_sw128(uint32_t tile, int r0, int c0, int lane, const uint32_t (&w)[16],
+                                                        uint8_t* dst, long long row_stride_bytes, int valid_rows) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    sts128(tile + sw128_offset(r0 + lane, c0 + c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = 8 * k + (lane >> 2);
+    const float4 v = lds128f(tile + sw128_offset(r0 + row, c0 + c));
+    if (row < valid_rows) *reinterpret_cast<float4*>(dst + row * row_stride_bytes + c * 16) = v;
+  }
+  __syncwarp();
+}
+
 }  // namespace fcsa
