@@ -45,6 +45,11 @@
 #include <algorithm>
 #include <type_traits>
 
+// register split of the backward CTA (setmaxnreg): 4 compute warpgroups + 1 service warpgroup, 4 c + s = 5 x 96
+#ifndef FCSA_BWD_SVC_REGS
+#define FCSA_BWD_SVC_REGS 64
+#define FCSA_BWD_CMP_REGS 104
+#endif
 #ifndef FCSA_BWD_POLY_EVERY
 #define FCSA_BWD_POLY_EVERY 3   // backward exp stage: 1 of every N exp pairs runs on the FMA pipe (0 = none)
 #endif
@@ -414,6 +419,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr uint32_t TM_S = Cfg::TM_S, TM_DP = Cfg::TM_DP, TM_DV = Cfg::TM_DV, TM_DK = Cfg::TM_DK,
                      TM_DQ = Cfg::TM_DQ, TM_X = Cfg::TM_X;
   constexpr bool KV_IN_TMEM = (D == 64);
+  // D = 128 runs one item per CTA (grid = number of items): every item loop below is then a single pass that the
+  // compiler can see through (running tile index = tile index, no loop-carried item state in registers)
+  constexpr bool PERSIST = KV_IN_TMEM;
   constexpr bool AUG = Cfg::kAug;          // per-query constants enter through an extra K = 16 MMA step
 
   extern __shared__ uint8_t smem_raw[];
@@ -423,8 +431,9 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // passes through shared memory on its way to TMEM, so the next item's K is prefetched into it; the next
   // item's V follows into K's buffer when the last dQ MMA and the dK epilogue are done with it.
   const uint32_t sKV0 = smem_u32(smem + Cfg::kOffK);
-  auto buf_k = [&](int n) { return sKV0 + ((n & 1) ? Cfg::kKV : 0); };
-  auto buf_v = [&](int n) { return sKV0 + ((n & 1) ? 0 : Cfg::kKV); };
+  // (D = 128: one item per CTA, K and V stay where they are - and their descriptors stay compile-time offsets)
+  auto buf_k = [&](int n) { return sKV0 + ((KV_IN_TMEM && (n & 1)) ? Cfg::kKV : 0); };
+  auto buf_v = [&](int n) { return sKV0 + ((KV_IN_TMEM && (n & 1)) ? 0 : Cfg::kKV); };
   const uint32_t sQ = smem_u32(smem + Cfg::kOffQ);
   const uint32_t sDO = smem_u32(smem + Cfg::kOffDO);
   const uint32_t sDS = smem_u32(smem + Cfg::kOffDS);
@@ -523,13 +532,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   pdl_wait();          // slivers / stats come from the preprocess kernel; accumulators are zero on entry
 
   if (wg == 4) {
-    reg_dealloc<64>();
+    reg_dealloc<FCSA_BWD_SVC_REGS>();
     if (warp == 19) {
       // =============================== K / V producer ==============================
       // (a thread of its own: its waits - V copied to TMEM, K's buffer released - must not hold up the ring)
       if (elect_one()) {
-        for (int n = 0;; ++n) {
-          const int idx = item_index(n);
+        for (int n = 0; PERSIST || n == 0; ++n) {
+          const int idx = PERSIST ? item_index(n) : static_cast<int>(blockIdx.x);
           if (idx < 0) break;
           const Item it = load_item(idx);
           if (n > 0) {
@@ -552,8 +561,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // =============================== Q / dO ring producer =======================
       if (elect_one()) {
         int tq = 0;                                 // query tiles so far, over all items (ring position)
-        for (int n = 0;; ++n) {
-          const int idx = item_index(n);
+        for (int n = 0; PERSIST || n == 0; ++n) {
+          const int idx = PERSIST ? item_index(n) : static_cast<int>(blockIdx.x);
           if (idx < 0) break;
           const Item it = load_item(idx);
           for (int i = 0; i < it.NI; ++i, ++tq) {
@@ -628,8 +637,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         int tq = 0;                                 // query tiles so far, over all items
         if (warp == 17) {
           // chain A: everything that does not depend on dS.
-          for (int n = 0;; ++n) {
-            const int idx = item_index(n);
+          for (int n = 0; PERSIST || n == 0; ++n) {
+            const int idx = PERSIST ? item_index(n) : static_cast<int>(blockIdx.x);
             if (idx < 0) break;
             const Item it = load_item(idx);
             const int NI = it.NI;
@@ -702,8 +711,8 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         } else {
           // chain B: the consumers of dS(i).  dK reads it from TMEM (the dQ accumulator columns),
           // then dQ(i) overwrites those columns - same issuing thread, in-order pipe.
-          for (int n = 0;; ++n) {
-            const int idx = item_index(n);
+          for (int n = 0; PERSIST || n == 0; ++n) {
+            const int idx = PERSIST ? item_index(n) : static_cast<int>(blockIdx.x);
             if (idx < 0) break;
             const Item it = load_item(idx);
             const int NI = it.NI;
@@ -754,7 +763,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // Splitting by columns (not by stage) puts four warps on every scheduler, all working on the
     // same tile: the TMEM / MUFU / shared-memory latencies of one warp hide under the others, and
     // P^T never makes a round trip through TMEM.
-    reg_alloc<104>();   // 4 x 104 + 64 = 5 x 96: the pool is what the CTA was launched with (640 x 96)
+    reg_alloc<FCSA_BWD_CMP_REGS>();   // 4 x compute + service = 5 x 96: the pool is what the CTA was launched with (640 x 96)
     const int wq = warp & 3;
     const int r = wq * 32 + lane;            // key row inside the tile
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
@@ -765,7 +774,19 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tP = lane_base + TM_DP + cq0;             // packed P^T goes over the dP^T columns this thread has read
     const uint32_t tDQ = lane_base + TM_DQ + 16 * wg;       // 16 dQ accumulator columns drained by this warpgroup
     const uint32_t tDS = tDQ;                                // ... which also hold its packed dS^T (CW/2 columns)
-    const uint32_t my_stage = sDQ + wq * 8192 + wg * 2048;     // 2 KB of dQ staging per warp
+    uint32_t my_stage = sDQ + wq * 8192 + wg * 2048;           // 2 KB of dQ staging per warp
+#ifndef FCSA_EXP_NO_PIN
+    // Pin the per-thread addresses of the tile loop in registers: inside the item loop the compiler otherwise
+    // re-derives them from tmem / the shared-memory base / the warp index in EVERY tile (rematerialisation),
+    // +10 % instructions in the loop.  An empty asm with a "+r" operand makes the value opaque.
+    uint32_t tS_p = tS, tDP_p = tDP, tDQ_p = tDQ;
+    asm volatile("" : "+r"(tS_p), "+r"(tDP_p), "+r"(tDQ_p), "+r"(my_stage));
+#define tS tS_p
+#define tDP tDP_p
+#define tP tDP_p
+#define tDQ tDQ_p
+#define tDS tDQ_p
+#endif
     const bool tr_lane = (wg == 0 && wq == 0 && lane == 0);
     auto ld_cw = [&](uint32_t addr, uint32_t (&dst)[CW]) {
       if constexpr (CW == 32) tmem_ld_x32(addr, dst);
@@ -807,10 +828,10 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     int prev_tile = -1;                      // accumulator tile of the previous query tile: drained one tile late
     int tq = 0;                              // query tiles so far, over all items
     const float c1 = a.c1;
-    for (int n = 0;; ++n) {
+    for (int n = 0; PERSIST || n == 0; ++n) {
     // (broadcast from lane 0: tells the compiler that everything derived from the item is warp-uniform, so the
     //  barrier waits of the tile loop stay on the uniform datapath, without reconvergence points)
-    const int idx = __shfl_sync(0xFFFFFFFFu, item_index(n), 0);
+    const int idx = PERSIST ? __shfl_sync(0xFFFFFFFFu, item_index(n), 0) : static_cast<int>(blockIdx.x);
     if (idx < 0) break;
     const Item it = load_item(idx);
     // (only what the tile loop needs stays live across it; the epilogue re-derives batch / head from idx)
@@ -851,7 +872,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int i = 0; i < NI; ++i) {
         // running tile index: ring stage and barrier parities (the broadcast keeps it, and every wait below,
         // on the uniform datapath - a loop-carried sum over items is not recognised as warp-uniform)
-        const int t = __shfl_sync(0xFFFFFFFFu, tq + i, 0);
+        const int t = PERSIST ? __shfl_sync(0xFFFFFFFFu, tq + i, 0) : i;
         const int st = t % NST, qt = i_lo + i;
         const int row0 = qt * QT;
         const uint32_t c3a = sStats + st * 1024 + cq0 * 4;           // c3 of this warpgroup's queries
@@ -974,7 +995,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         // ---- dQ(i-1) out of its accumulator columns (its MMA sits right behind dK(i-1): long done;
         // it has also released the shared-memory dS^T), then dS^T(i) into them
-        if (prev_tile >= 0) load_dq(t - 1);
+        if (t > 0) load_dq(t - 1);            // (t is warp-uniform by construction: no reconvergence code)
         if (tr_lane) FCSA_TR(2, i, 2);
         st_cw(tDS, ds);
         // the same CW queries -> shared memory: row = key, query-contiguous 64-wide chunks, 128B swizzle
@@ -991,7 +1012,7 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (tr_lane) FCSA_TR(2, i, 3);
         if (i == 0) FCSA_ITEM_T(tr_lane, idx, 3);
         if (i == NI - 1) FCSA_ITEM_T(tr_lane, idx, 4);
-        if (prev_tile >= 0) reduce_dq(prev_tile);
+        if (t > 0) reduce_dq(prev_tile);
         prev_tile = tile0 + qt;
       }
       tq += NI;
@@ -1131,6 +1152,13 @@ fcsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncwarp();
   }
 
+#ifndef FCSA_EXP_NO_PIN
+#undef tS
+#undef tDP
+#undef tP
+#undef tDQ
+#undef tDS
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem, 512);

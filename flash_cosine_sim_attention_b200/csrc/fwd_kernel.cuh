@@ -28,6 +28,12 @@
 
 #include "sm100_primitives.cuh"
 
+#ifndef FCSA_FWD_SVC_REGS_64
+#define FCSA_FWD_SVC_REGS_64 64
+#endif
+#ifndef FCSA_FWD_SVC_REGS_128
+#define FCSA_FWD_SVC_REGS_128 96   // D = 128: no re-budgeting - with 64 the MMA issuers spill, and their reloads sit on the serial S -> P -> PV chain (1050 vs 850 us at (1,16,16384,128))
+#endif
 #ifndef FCSA_POLY_EVERY
 #define FCSA_POLY_EVERY 4   // forward, D = 64: 1 of every N exp pairs runs on the FMA pipe (0 = none)
 #endif
@@ -187,7 +193,14 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #endif
   pdl_wait();          // q, k (normalised by the previous kernel), v, mask are read from here on
 
-  if (warp >= 16) reg_dealloc<64>();      // 4 x 104 + 64 = 5 x 96: the pool is what the CTA was launched with
+  // register split: 4 softmax warpgroups x kSmxRegs + the service warpgroup x kSvcRegs = 5 x 96, the pool the CTA was
+  // launched with (640 threads x 96)
+  constexpr int kSvcRegs = (D == 64) ? FCSA_FWD_SVC_REGS_64 : FCSA_FWD_SVC_REGS_128;
+  constexpr int kSmxRegs = (5 * 96 - kSvcRegs) / 4;
+  static_assert(kSmxRegs % 8 == 0, "setmaxnreg wants multiples of 8");
+  if constexpr (kSvcRegs < 96) {
+    if (warp >= 16) reg_dealloc<kSvcRegs>();
+  }
   if (warp == 16) {
     // =============================== TMA producer ===============================
     // (elect_one, not lane == 0: ptxas then keeps descriptors/addresses in uniform registers
@@ -321,7 +334,7 @@ fcsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp < 16) {
     // =============================== softmax warpgroups =========================
-    reg_alloc<104>();
+    if constexpr (kSmxRegs > 96) reg_alloc<kSmxRegs>();
     const int t = warp >> 3;                 // which 128-row tile
     const int half = (warp >> 2) & 1;        // which 64 of the 128 key columns of every tile
     const int wq = warp & 3;                 // TMEM lane quarter this warp may touch

@@ -23,7 +23,11 @@ __global__ void fill(__nv_bfloat16* p, size_t n, unsigned seed, float amp) {
 int main(int argc, char** argv) {
   // usage: [B H Nq Nk causal]  (default: the benchmark shape).  Without -DFCSA_TRACE this is a plain
   // timing harness (A/B experiments): ... -o time_fwd trace_fwd.cu
-  const int B = argc > 1 ? atoi(argv[1]) : 4, H = argc > 2 ? atoi(argv[2]) : 8, D = 64;
+  const int B = argc > 1 ? atoi(argv[1]) : 4, H = argc > 2 ? atoi(argv[2]) : 8;
+#ifndef FCSA_HARNESS_D
+#define FCSA_HARNESS_D 64
+#endif
+  constexpr int D = FCSA_HARNESS_D;
   const int Nq = argc > 3 ? atoi(argv[3]) : 4096, Nk = argc > 4 ? atoi(argv[4]) : 4096;
   const int causal = argc > 5 ? atoi(argv[5]) : 1;
   const int grid_arg = argc > 6 ? atoi(argv[6]) : 148;    // CTAs (persistent); 0 = one CTA per work item
