@@ -10,16 +10,20 @@
 // The machine mapping is new.  Three kernels:
 //   1. bwd_prep_kernel    : per query row {c3 = log2(inv_l) - shift*log2e, delta} (fp32, never
 //                           rounded to 16 bit as the reference does at cu:1260/1820), for D = 64 also as
-//                           16-bit "slivers" (see 2.); zeroes the dQ accumulator
-//   2. fcsa_bwd_kernel    : one CTA per (key tile of 128, batch, head), key/value tile stationary,
-//                           loop over query tiles of QT rows.  Everything is computed TRANSPOSED
+//                           16-bit "slivers" (see 2.)
+//   2. fcsa_bwd_kernel    : work item = (key tile of 128, batch, head), key/value tile stationary, loop over the
+//                           query tiles of QT rows that can see it.  D = 64: persistent CTAs (one per SM) walk the
+//                           items - continuous query-tile stream, next K prefetched into V's shared-memory buffer,
+//                           dQ drain of an item's last tile under the next item's first, dV/dK epilogue of one item
+//                           under the first MMAs of the next; D = 128: one item per CTA.  Everything is computed TRANSPOSED
 //                           (rows = keys): S^T = K Q^T and dP^T = V dO^T so that P^T and dS^T land in
 //                           TMEM exactly in the layout tcgen05 wants for an A operand (dV += P^T dO,
 //                           dK += dS^T Q read A from TMEM); dS is also staged in shared memory for the
 //                           dQ product.  dQ partial tiles leave through shared memory and a TMA bulk
 //                           reduce-add into an fp32 accumulator - no per-element global atomics
 //                           (reference: cu:1602-1610).
-//   3. bwd_dq_finish_kernel: fp32 accumulator * scale -> 16-bit dq (+ l2norm backward of q).
+//   3. bwd_dq_finish_kernel: fp32 accumulator * scale -> 16-bit dq (+ l2norm backward of q); writes the accumulator
+//                           back as zeros (the "zeroed" workspace is zero on entry and on exit of every call).
 //
 // The main kernel is bound by shared-memory bandwidth (MMA operand fetch, TMA fills and the element-wise
 // warps' own traffic share 128 B/clk), so its structure minimises shared-memory accesses:
@@ -302,9 +306,6 @@ __device__ __forceinline__ uint32_t ldg_u16(const void* p) {
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-__device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // 16-byte load served by L2 (never a stale L1 line): accumulator tiles other CTAs have reduced into
 __device__ __forceinline__ float4 ldg_cg128f(const float* p) {

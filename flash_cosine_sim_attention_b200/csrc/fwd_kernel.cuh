@@ -5,8 +5,11 @@
 // final 1/max(l, eps) scaling, cu:1239-1246; bottom-right aligned causal mask, cu:1097/1210;
 // key-padding mask, cu:1198-1212) - completely different machine mapping:
 //
-//   * one CTA owns 256 query rows of one (batch, head): two 128-row tiles that ping-pong
-//   * warp 16  : TMA producer   (Q once, K and V tiles through mbarrier rings)
+//   * one work item = 256 query rows of one (batch, head): two 128-row tiles that ping-pong, each with its own
+//     "engine" (MMA issuer + 8 softmax warps).  Persistent CTAs, one per SM, walk the items (heaviest first, snake
+//     order): TMEM, barriers and the K/V ring live on, the next item's Q/K/V are prefetched, one tile's epilogue
+//     runs under the other tile's MMAs
+//   * warp 16  : TMA producer   (Q per item and tile, K and V tiles through mbarrier rings)
 //   * warps 17,18: tcgen05 issuers, one per query tile (S_t = Q_t K_j^T into TMEM; O_t += P_t V_j with
 //                P_t read from TMEM); warp 19 idles
 //   * warps 0-7: "softmax" warps of tile 0, warps 8-15 of tile 1.  Per tile two warpgroups, each on
