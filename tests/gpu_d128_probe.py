@@ -1,3 +1,7 @@
+"""Forward-only and forward+backward time of the two D = 128 shapes (C5 per-GPU share, (4,8,4096,128)) through the
+public API - the probe that separated the D = 128 forward regression (MMA-issuer spills) from the backward's.
+FCSA_OLD_PKG=1 imports a package copy from _scratch_r1/old_pkg (a build of an earlier commit staged by hand) for a
+same-box comparison.  Run under gpurun:  python tests/gpu_d128_probe.py"""
 import os, sys, torch
 sys.path.insert(0, "_scratch_r1/old_pkg" if os.environ.get("FCSA_OLD_PKG") else ".")
 from flash_cosine_sim_attention_b200 import flash_cosine_sim_attention
